@@ -1,0 +1,224 @@
+// Flash-style scaled-dot-product attention on tcgen05/TMEM (no mask, scale = d^-0.5), the op the reference
+// reaches through xformers.memory_efficient_attention (call shape witnessed at
+// /root/reference/diffmining/applications/parallel-dataset/pnp.py:440-442).
+//
+// One CTA = one (batch, head, 128-query tile); 128 threads, thread r owns query row r.
+//   S  = Q K^T      tcgen05.mma, Q/K tiles TMA-staged (K-major, 128B swizzle), S fp32 in TMEM
+//   P  = softmax    row r read from TMEM by thread r (no shuffles), fp32 running max/sum, exp2 with the
+//                   d^-0.5*log2(e) scale folded in, P rounded to fp16 into a swizzled smem tile
+//   O += P V        tcgen05.mma, V tile consumed as an MN-major operand straight from its natural [key][d]
+//                   layout; O (fp32) lives in TMEM and is rescaled there only when a row max moved
+// head_dim 40/80/160 are zero-padded to 48/80/160 by TMA out-of-bounds fill (tensor maps are rank-4
+// (d, head, token, batch), so the pad never reads the neighbouring head).  Two CTAs are co-resident per SM
+// so one CTA's softmax overlaps the other's MMAs.
+#pragma once
+#include "ptx.cuh"
+
+namespace dm {
+
+struct alignas(64) AttnMaps {
+  CUtensorMap q, k, v;
+};
+
+struct AttnParams {
+  int Tq, Tk, B, heads;
+  const int* kv_index;  // [B] batch -> K/V batch coordinate (context slot); null = identity
+  __half* out;          // [B, Tq, ld_out] ; head h occupies columns [h*D, (h+1)*D)
+  long long ld_out;
+  float scale_log2;     // d^-0.5 * log2(e)
+};
+
+template <int D, int BKV>
+struct AttnCfg {
+  static constexpr int DK = (D + 15) / 16 * 16;  // K extent of QK^T and N extent of PV
+  static constexpr int NCH = (D + 63) / 64;      // 64-wide d chunks
+  static constexpr int Q_BYTES = NCH * 128 * 128;
+  static constexpr int KV_BYTES = NCH * BKV * 128;
+  static constexpr int P_BYTES = 128 * BKV * 2;
+  static constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_BYTES + P_BYTES + 1024 + 128;
+  static constexpr int O_COL = BKV;  // S occupies TMEM columns [0, BKV)
+  static constexpr int TMEM_COLS = (BKV + DK <= 128) ? 128 : (BKV + DK <= 256) ? 256 : 512;
+};
+
+template <int D, int BKV>
+__global__ void __launch_bounds__(128, 1) attention_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
+  using Cfg = AttnCfg<D, BKV>;
+  constexpr int DK = Cfg::DK, NCH = Cfg::NCH;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + Cfg::KV_BYTES;
+  uint8_t* sP = sV + Cfg::KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t *bar_q = bars, *bar_k = bars + 1, *bar_v = bars + 2, *bar_s = bars + 3, *bar_o = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
+  const int kvb = p.kv_index ? p.kv_index[b] : b;
+  const int nkv = (p.Tk + BKV - 1) / BKV;
+
+  if (tid == 0) {
+    mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&maps.q); tma_prefetch_desc(&maps.k); tma_prefetch_desc(&maps.v);
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);  // this thread's lane quarter
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, Cfg::Q_BYTES);
+    for (int c = 0; c < NCH; ++c) tma_load_4d(sQ + c * 16384, &maps.q, bar_q, c * 64, head, q0, b);
+    mbar_arrive_expect_tx(bar_k, Cfg::KV_BYTES);
+    for (int c = 0; c < NCH; ++c) tma_load_4d(sK + c * BKV * 128, &maps.k, bar_k, c * 64, head, 0, kvb);
+    mbar_arrive_expect_tx(bar_v, Cfg::KV_BYTES);
+    for (int c = 0; c < NCH; ++c) tma_load_4d(sV + c * BKV * 128, &maps.v, bar_v, c * 64, head, 0, kvb);
+    mbar_wait(bar_q, 0);
+  }
+
+  float m_run = -INFINITY, l_run = 0.f;
+  constexpr uint32_t idesc_s = umma_idesc_f16(BKV, false);
+  constexpr uint32_t idesc_o = umma_idesc_f16(DK, true);
+
+  for (int j = 0; j < nkv; ++j) {
+    const uint32_t ph = j & 1;
+    if (tid == 0) {
+      mbar_wait(bar_k, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < DK / 16; ++ks) {
+        const uint64_t ad = umma_desc_kmajor_sw128(smem_u32(sQ + (ks >> 2) * 16384)) + 2 * (ks & 3);
+        const uint64_t bd = umma_desc_kmajor_sw128(smem_u32(sK + (ks >> 2) * BKV * 128)) + 2 * (ks & 3);
+        umma_f16(tmem_base, ad, bd, idesc_s, ks != 0 ? 1u : 0u);
+      }
+      umma_commit(bar_s);
+    }
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+    if (tid == 0 && j + 1 < nkv) {  // K tile is free again: prefetch the next one under the softmax
+      mbar_arrive_expect_tx(bar_k, Cfg::KV_BYTES);
+      for (int c = 0; c < NCH; ++c) tma_load_4d(sK + c * BKV * 128, &maps.k, bar_k, c * 64, head, (j + 1) * BKV, kvb);
+    }
+    const int kbase = j * BKV;
+    const bool need_mask = kbase + BKV > p.Tk;
+    // ---- pass 1: row max
+    float mx = m_run;
+#pragma unroll
+    for (int c0 = 0; c0 < BKV; c0 += 32) {
+      uint32_t raw[32];
+      tmem_ld_x32(t_row + c0, raw);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float s = __uint_as_float(raw[i]);
+        if (need_mask && kbase + c0 + i >= p.Tk) s = -INFINITY;
+        mx = fmaxf(mx, s);
+      }
+    }
+    const float m_new = mx;  // finite: every tile has >= 1 valid key
+    const float alpha = exp2f((m_run - m_new) * p.scale_log2);
+    const float moff = m_new * p.scale_log2;
+    // previous PV must be done before P (its A operand) is overwritten / O is rescaled
+    if (j > 0) {
+      mbar_wait(bar_o, (j - 1) & 1);
+      tc_fence_after();
+      if (tid == 0) {  // V tile free: prefetch
+        mbar_arrive_expect_tx(bar_v, Cfg::KV_BYTES);
+        for (int c = 0; c < NCH; ++c) tma_load_4d(sV + c * BKV * 128, &maps.v, bar_v, c * 64, head, j * BKV, kvb);
+      }
+    }
+    // ---- pass 2: P = exp2(S*scale - m*scale) -> fp16 swizzled smem, row sum
+    float lsum = 0.f;
+#pragma unroll
+    for (int c0 = 0; c0 < BKV; c0 += 32) {
+      uint32_t raw[32];
+      tmem_ld_x32(t_row + c0, raw);
+      tmem_wait_ld();
+      float pv[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float s = __uint_as_float(raw[i]);
+        float e = fast_exp2(s * p.scale_log2 - moff);
+        if (need_mask && kbase + c0 + i >= p.Tk) e = 0.f;
+        pv[i] = e;
+        lsum += e;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        const int k = c0 + i;
+        const uint32_t off = (k >> 6) * 16384 + tid * 128 + ((((k & 63) >> 3) ^ (tid & 7)) << 4);
+        *reinterpret_cast<uint4*>(sP + off) = make_uint4(pack_h2(pv[i], pv[i + 1]), pack_h2(pv[i + 2], pv[i + 3]),
+                                                         pack_h2(pv[i + 4], pv[i + 5]), pack_h2(pv[i + 6], pv[i + 7]));
+      }
+    }
+    l_run = l_run * alpha + lsum;
+    m_run = m_new;
+    // ---- rescale O in TMEM when this warp saw a max move
+    if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.f)) {
+#pragma unroll
+      for (int c0 = 0; c0 < DK; c0 += 16) {
+        uint32_t raw[16];
+        tmem_ld_x16(t_row + Cfg::O_COL + c0, raw);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
+        tmem_st_x16(t_row + Cfg::O_COL + c0, raw);
+      }
+      tmem_wait_st();
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(bar_v, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < BKV / 16; ++ks) {
+        const uint64_t ad = umma_desc_kmajor_sw128(smem_u32(sP + (ks >> 2) * 16384)) + 2 * (ks & 3);
+        const uint64_t bd = umma_desc_mnmajor_sw128(smem_u32(sV + ks * 2048), BKV * 128);
+        umma_f16(tmem_base + Cfg::O_COL, ad, bd, idesc_o, (j | ks) != 0 ? 1u : 0u);
+      }
+      umma_commit(bar_o);
+    }
+  }
+  mbar_wait(bar_o, (nkv - 1) & 1);
+  tc_fence_after();
+  const int q = q0 + tid;
+  const float inv = 1.f / l_run;
+  __half* orow = p.out + (static_cast<long long>(b) * p.Tq + q) * p.ld_out + head * D;
+#pragma unroll
+  for (int c0 = 0; c0 < DK; c0 += 16) {
+    uint32_t raw[16];
+    tmem_ld_x16(t_row + Cfg::O_COL + c0, raw);
+    tmem_wait_ld();
+    if (q < p.Tq) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 8) {
+        if (c0 + i < D) {
+          *reinterpret_cast<uint4*>(orow + c0 + i) =
+              make_uint4(pack_h2(__uint_as_float(raw[i]) * inv, __uint_as_float(raw[i + 1]) * inv),
+                         pack_h2(__uint_as_float(raw[i + 2]) * inv, __uint_as_float(raw[i + 3]) * inv),
+                         pack_h2(__uint_as_float(raw[i + 4]) * inv, __uint_as_float(raw[i + 5]) * inv),
+                         pack_h2(__uint_as_float(raw[i + 6]) * inv, __uint_as_float(raw[i + 7]) * inv));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace dm

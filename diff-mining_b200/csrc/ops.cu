@@ -1,0 +1,318 @@
+// Host-side preparation + launch of every kernel (see ops.h).
+#include "ops.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "misc.cuh"
+#include "norm.cuh"
+
+namespace dm {
+
+// ------------------------------------------------------------------ tensor maps
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  DM_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  return fn;
+}
+
+// fp16 tensor, dims innermost-first, strides (bytes) for dims 1..rank-1, 128B swizzle, zero OOB fill
+static void make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_b,
+                      const uint32_t* box) {
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    DM_CHECK(dims[i] > 0 && box[i] > 0 && box[i] <= 256, "tensor map: bad dim/box");
+  }
+  for (int i = 0; i < rank - 1; ++i) {
+    gs[i] = strides_b[i];
+    DM_CHECK(gs[i] % 16 == 0, "tensor map: stride not a multiple of 16 bytes");
+  }
+  DM_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "tensor map: base not 16-byte aligned");
+  CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
+}
+
+// ------------------------------------------------------------------ igemm
+void seg_conv3x3(IgemmDesc& d, int Cin_total, int C0) {
+  d.nseg = 0;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    IgSeg s{};
+    s.src = 0; s.dy = dy; s.dx = dx; s.dn = 0; s.chan0 = 0; s.nchunks = C0 / 64;
+    d.seg[d.nseg++] = s;
+    if (Cin_total > C0) {
+      s.src = 1; s.nchunks = (Cin_total - C0) / 64;
+      d.seg[d.nseg++] = s;
+    }
+  }
+}
+void seg_conv3x3_s2(IgemmDesc& d, int C, int Nimg, bool vae_pad) {
+  // src0 = parity planes [(py*2+px)*Nimg + n, H2, W2, C]
+  static const int unet_par[3] = {1, 0, 1}, unet_off[3] = {-1, 0, 0};  // pad 1:   in = 2*out + r - 1
+  static const int vae_par[3] = {0, 1, 0}, vae_off[3] = {0, 0, 1};     // pad 0/1: in = 2*out + r
+  const int* par = vae_pad ? vae_par : unet_par;
+  const int* off = vae_pad ? vae_off : unet_off;
+  d.nseg = 0;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int r = tap / 3, c = tap % 3;
+    IgSeg s{};
+    s.src = 0; s.dy = off[r]; s.dx = off[c]; s.dn = (par[r] * 2 + par[c]) * Nimg; s.chan0 = 0; s.nchunks = C / 64;
+    d.seg[d.nseg++] = s;
+  }
+}
+void seg_1x1(IgemmDesc& d, int C0, int C1) {
+  d.nseg = 0;
+  IgSeg s{};
+  s.src = 0; s.nchunks = C0 / 64;
+  d.seg[d.nseg++] = s;
+  if (C1 > 0) {
+    s.src = 1; s.nchunks = C1 / 64;
+    d.seg[d.nseg++] = s;
+  }
+}
+
+static int pick_bn(int N) {
+  static const int cand[] = {256, 160, 128, 64, 32, 16};
+  int best = 16;
+  long long best_pad = -1;
+  for (int bn : cand) {
+    const long long pad = static_cast<long long>((N + bn - 1) / bn) * bn;
+    if (best_pad < 0 || pad < best_pad) { best_pad = pad; best = bn; }
+  }
+  return best;
+}
+
+IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms) {
+  IgemmOp op{};
+  IgParams& p = op.p;
+  DM_CHECK(d.nseg > 0 && d.nseg <= IG_MAX_SEG, "igemm: bad segment count");
+  DM_CHECK(d.N % 8 == 0 && d.N >= 16, "igemm: N must be a multiple of 8 and >= 16");
+  int kit = 0;
+  for (int i = 0; i < d.nseg; ++i) {
+    DM_CHECK(d.seg[i].src < d.nsrc, "igemm: segment source out of range");
+    kit += d.seg[i].nchunks;
+    p.seg[i] = d.seg[i];
+  }
+  DM_CHECK(kit * IG_BK == d.K, "igemm: K (" + std::to_string(d.K) + ") != 64 * chunks (" + std::to_string(kit) + ")");
+  p.nseg = d.nseg;
+  p.k_iters = kit;
+  p.Nimg = d.Nimg; p.H = d.H; p.W = d.W;
+  // M-tile shape: 2^wt x 2^ht x 2^nt = 128 pixels, minimal padding, widest rows preferred
+  long long best = -1;
+  for (int wl = 7; wl >= 0; --wl)
+    for (int hl = 7 - wl; hl >= 0; --hl) {
+      const int nl = 7 - wl - hl;
+      const long long wt = 1 << wl, ht = 1 << hl, nt = 1 << nl;
+      const long long pad = ((d.W + wt - 1) / wt * wt) * ((d.H + ht - 1) / ht * ht) * ((d.Nimg + nt - 1) / nt * nt);
+      if (best < 0 || pad < best) { best = pad; p.wt_log = wl; p.ht_log = hl; p.nt_log = nl; }
+    }
+  const int wt = 1 << p.wt_log, ht = 1 << p.ht_log, nt = 1 << p.nt_log;
+  p.tiles_x = (d.W + wt - 1) / wt;
+  p.tiles_y = (d.H + ht - 1) / ht;
+  p.tiles_n = (d.Nimg + nt - 1) / nt;
+  p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  op.bn = d.bn ? d.bn : pick_bn(d.N);
+  p.n_tiles = (d.N + op.bn - 1) / op.bn;
+  p.N = d.N;
+  p.bias = d.bias; p.rowbias = d.rowbias; p.ld_rowbias = d.ld_rowbias;
+  p.residual = d.residual; p.ld_res = d.ld_res;
+  p.out = d.out; p.ld_out = d.ld_out;
+  p.out_f32 = d.out_f32; p.geglu = d.geglu; p.act_silu = d.act_silu;
+  DM_CHECK(d.out != nullptr && d.ld_out % 8 == 0, "igemm: bad output");
+  for (int s = 0; s < d.nsrc; ++s) {
+    const ActView& a = d.src[s];
+    DM_CHECK(a.ptr && a.C > 0 && a.pix_stride >= a.C, "igemm: bad source view");
+    const uint64_t dims[4] = {static_cast<uint64_t>(a.C), static_cast<uint64_t>(a.W), static_cast<uint64_t>(a.H),
+                              static_cast<uint64_t>(a.N)};
+    const uint64_t st[3] = {static_cast<uint64_t>(a.pix_stride) * 2, static_cast<uint64_t>(a.pix_stride) * 2 * a.W,
+                            static_cast<uint64_t>(a.pix_stride) * 2 * a.W * a.H};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(wt), static_cast<uint32_t>(ht), static_cast<uint32_t>(nt)};
+    make_tmap(&op.maps.a[s], a.ptr, 4, dims, st, box);
+  }
+  if (d.nsrc == 1) op.maps.a[1] = op.maps.a[0];
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.N)};
+    const uint64_t st[1] = {static_cast<uint64_t>(d.K) * 2};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(op.bn)};
+    make_tmap(&op.maps.b, d.Wt, 2, dims, st, box);
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  op.grid = std::min(tiles, num_sms);
+  op.flops = 2.0 * d.Nimg * d.H * d.W * static_cast<double>(d.N) * d.K;
+  return op;
+}
+
+template <int BN>
+static void igemm_launch_bn(const IgemmOp& op, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    DM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, IgCfg<BN>::SMEM_BYTES));
+    configured = true;
+  }
+  igemm_kernel<BN><<<op.grid, 192, IgCfg<BN>::SMEM_BYTES, s>>>(op.maps, op.p);
+  DM_CUDA(cudaGetLastError());
+}
+
+void igemm_launch(const IgemmOp& op, cudaStream_t s) {
+  switch (op.bn) {
+    case 256: igemm_launch_bn<256>(op, s); break;
+    case 160: igemm_launch_bn<160>(op, s); break;
+    case 128: igemm_launch_bn<128>(op, s); break;
+    case 64: igemm_launch_bn<64>(op, s); break;
+    case 32: igemm_launch_bn<32>(op, s); break;
+    case 16: igemm_launch_bn<16>(op, s); break;
+    default: DM_CHECK(false, "igemm: unsupported BN " + std::to_string(op.bn));
+  }
+}
+
+// ------------------------------------------------------------------ attention
+AttnOp attn_prepare(const AttnDesc& d) {
+  AttnOp op{};
+  DM_CHECK(d.D == 40 || d.D == 80 || d.D == 160, "attention: head_dim must be 40, 80 or 160");
+  DM_CHECK(d.Tq > 0 && d.Tk > 0 && d.B > 0, "attention: empty problem");
+  op.D = d.D;
+  const int bkv = d.D == 40 ? 128 : 64;
+  auto mk = [&](CUtensorMap* m, const __half* ptr, long long ld, long long bs, int T, int nb, int rows) {
+    const uint64_t dims[4] = {static_cast<uint64_t>(d.D), static_cast<uint64_t>(d.heads), static_cast<uint64_t>(T),
+                              static_cast<uint64_t>(nb)};
+    const uint64_t st[3] = {static_cast<uint64_t>(d.D) * 2, static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(bs) * 2};
+    const uint32_t box[4] = {64, 1, static_cast<uint32_t>(rows), 1};
+    make_tmap(m, ptr, 4, dims, st, box);
+  };
+  const int kvb = d.kv_batches ? d.kv_batches : d.B;
+  mk(&op.maps.q, d.q, d.ld_q, d.bs_q, d.Tq, d.B, 128);
+  mk(&op.maps.k, d.k, d.ld_k, d.bs_k, d.Tk, kvb, bkv);
+  mk(&op.maps.v, d.v, d.ld_v, d.bs_v, d.Tk, kvb, bkv);
+  op.p.Tq = d.Tq; op.p.Tk = d.Tk; op.p.B = d.B; op.p.heads = d.heads;
+  op.p.kv_index = d.kv_index;
+  op.p.out = d.out; op.p.ld_out = d.ld_out;
+  op.p.scale_log2 = static_cast<float>(1.0 / std::sqrt(static_cast<double>(d.D)) * 1.4426950408889634);
+  op.grid = dim3((d.Tq + 127) / 128, d.heads, d.B);
+  op.flops = 4.0 * d.B * d.heads * static_cast<double>(d.Tq) * d.Tk * d.D;
+  return op;
+}
+
+template <int D, int BKV>
+static void attn_launch_d(const AttnOp& op, cudaStream_t s) {
+  static bool configured = false;
+  using Cfg = AttnCfg<D, BKV>;
+  if (!configured) {
+    DM_CUDA(cudaFuncSetAttribute(attention_kernel<D, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  attention_kernel<D, BKV><<<op.grid, 128, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
+  DM_CUDA(cudaGetLastError());
+}
+void attn_launch(const AttnOp& op, cudaStream_t s) {
+  switch (op.D) {
+    case 40: attn_launch_d<40, 128>(op, s); break;
+    case 80: attn_launch_d<80, 64>(op, s); break;
+    case 160: attn_launch_d<160, 64>(op, s); break;
+    default: DM_CHECK(false, "attention: unsupported head_dim");
+  }
+}
+
+// ------------------------------------------------------------------ norms / misc
+static int grid_for(long long total, int block = 256, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  return static_cast<int>(std::max<long long>(1, std::min<long long>(g, cap)));
+}
+
+int gn_splits(int Nimg, int HW) {
+  int s = std::max(1, (148 * 4 + Nimg - 1) / Nimg);
+  s = std::min(s, std::max(1, HW / 16));
+  return std::min(s, 64);
+}
+
+void gn_launch(const GnDesc& d, cudaStream_t s) {
+  const int C = d.C0 + d.C1;
+  DM_CHECK(C % 32 == 0 && d.C0 % 8 == 0 && d.C1 % 8 == 0, "groupnorm: channel counts must be multiples of 8 / 32");
+  const int cpg = C / 32;
+  const int splits = gn_splits(d.Nimg, d.HW);
+  NormSrc s0{d.src0, d.C0, d.ps0}, s1{d.src1, d.C1, d.ps1};
+  const int vcols = C / 8;
+  const int threads = vcols <= 256 ? vcols * (256 / vcols) : 256;
+  gn_stats_kernel<<<dim3(splits, d.Nimg), threads, 0, s>>>(s0, s1, d.HW, cpg, splits, d.partial);
+  DM_CUDA(cudaGetLastError());
+  const long long per_img = static_cast<long long>(d.HW) * vcols;
+  int chunks = static_cast<int>(std::min<long long>(std::max<long long>(1, per_img / 2048), 1024));
+  chunks = std::min(chunks, d.HW);
+  gn_apply_kernel<<<dim3(chunks, d.Nimg), 256, C * sizeof(float2), s>>>(s0, s1, d.HW, cpg, splits, d.partial, d.gamma,
+                                                                        d.beta, d.eps, d.silu, chunks, d.out);
+  DM_CUDA(cudaGetLastError());
+}
+
+void layernorm_launch(const __half* x, long long ld_x, const float* gamma, const float* beta, float eps, long long rows,
+                      int C, __half* out, long long ld_out, cudaStream_t s) {
+  DM_CHECK(C % 8 == 0 && C <= 1280, "layernorm: C must be a multiple of 8 and <= 1280");
+  const long long blocks = (rows + 7) / 8;
+  layernorm_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(x, ld_x, gamma, beta, eps, rows, C, out, ld_out);
+  DM_CUDA(cudaGetLastError());
+}
+
+void patch3x3_launch(const float* x0, const int* x_index, const float* noise, const int* noise_index, const long long* t,
+                     const float* ca, const float* cb, int Bf, int Cin, int H, int W, __half* out, cudaStream_t s) {
+  DM_CHECK(9 * Cin <= 64, "patch3x3: Cin too large");
+  patch3x3_kernel<<<grid_for(static_cast<long long>(Bf) * H * W * 8), 256, 0, s>>>(x0, x_index, noise, noise_index, t, ca,
+                                                                                   cb, Bf, Cin, H, W, out);
+  DM_CUDA(cudaGetLastError());
+}
+void timestep_embed_launch(const long long* t, const int* t_index, int Bf, __half* out, cudaStream_t s) {
+  timestep_embed_kernel<<<Bf, 160, 0, s>>>(t, t_index, Bf, out);
+  DM_CUDA(cudaGetLastError());
+}
+void upsample_nearest_launch(const __half* in, int N, int H, int W, int C, int Ho, int Wo, __half* out, cudaStream_t s) {
+  upsample_nearest_kernel<<<grid_for(static_cast<long long>(N) * Ho * Wo * (C / 8)), 256, 0, s>>>(in, N, H, W, C, Ho, Wo,
+                                                                                                  out);
+  DM_CUDA(cudaGetLastError());
+}
+void space_to_planes_launch(const __half* in, int N, int H, int W, int C, int H2, int W2, __half* out, cudaStream_t s) {
+  space_to_planes_kernel<<<grid_for(4ll * N * H2 * W2 * (C / 8)), 256, 0, s>>>(in, N, H, W, C, H2, W2, out);
+  DM_CUDA(cudaGetLastError());
+}
+void loss_launch(const __half* pred, int ld_pred, const float* noise, const int* noise_index, const int* grid_row,
+                 float* loss_f32, __half* grid_f16, float* eps_f32, int Bf, int HW, cudaStream_t s) {
+  LossMap mp{noise_index, grid_row, loss_f32, grid_f16, eps_f32};
+  loss_kernel<<<grid_for(static_cast<long long>(Bf) * HW), 256, 0, s>>>(pred, ld_pred, noise, mp, Bf, HW);
+  DM_CUDA(cudaGetLastError());
+}
+void tmap_launch(const __half* grid, int Bi, int N, int n_cond, int HW, float* T, cudaStream_t s) {
+  tmap_kernel<<<grid_for(static_cast<long long>(Bi) * (n_cond - 1) * HW), 256, 0, s>>>(grid, Bi, N, n_cond, HW, T);
+  DM_CUDA(cudaGetLastError());
+}
+void vae_sample_launch(const __half* h16, int ld_h, const __half* wq, const float* bq, const float* eps, float scaling,
+                       int B, int HW, float* z, float* mean_out, float* logvar_out, cudaStream_t s) {
+  vae_sample_kernel<<<grid_for(static_cast<long long>(B) * HW), 256, 0, s>>>(h16, ld_h, wq, bq, eps, scaling, B, HW, z,
+                                                                            mean_out, logvar_out);
+  DM_CUDA(cudaGetLastError());
+}
+void softmax_rows_launch(const float* S, long long ld_s, int rows, int cols, float scale, __half* P, long long ld_p,
+                         cudaStream_t s) {
+  softmax_rows_kernel<<<rows, 256, 0, s>>>(S, ld_s, cols, scale, P, ld_p);
+  DM_CUDA(cudaGetLastError());
+}
+void nhwc_to_nchw_mean_launch(const __half* in, int B, int E, int HW, int C, float* out, cudaStream_t s) {
+  nhwc_to_nchw_mean_kernel<<<dim3((HW + 31) / 32, (C + 31) / 32, B), 256, 0, s>>>(in, B, E, HW, C, out);
+  DM_CUDA(cudaGetLastError());
+}
+
+}  // namespace dm

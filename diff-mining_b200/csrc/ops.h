@@ -1,0 +1,120 @@
+// Host-side operator layer: prepares (tensor maps, tile shapes) and launches the CUDA kernels.
+// Ops are prepared once per plan (buffers are static inside the engine's arena) and replayed.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "attention.cuh"
+#include "igemm.cuh"
+
+namespace dm {
+
+struct DmError : std::runtime_error {
+  explicit DmError(const std::string& s) : std::runtime_error(s) {}
+};
+#define DM_CHECK(cond, msg)                                                                         \
+  do {                                                                                              \
+    if (!(cond)) throw ::dm::DmError(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + (msg)); \
+  } while (0)
+#define DM_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      throw ::dm::DmError(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + #expr + ": " + \
+                          cudaGetErrorString(e__));                                        \
+  } while (0)
+
+// ---- NHWC fp16 tensor view handed to TMA: dims as the conv sees them
+struct ActView {
+  const __half* ptr = nullptr;
+  int N = 1, H = 1, W = 1, C = 0;  // addressable extent
+  long long pix_stride = 0;        // elements between pixels (>= C)
+};
+
+struct IgemmDesc {
+  int Nimg = 1, H = 1, W = 1;  // output pixel grid
+  int nsrc = 1;
+  ActView src[2];
+  int nseg = 0;
+  IgSeg seg[IG_MAX_SEG];
+  const __half* Wt = nullptr;  // [N, K] K-major
+  int N = 0, K = 0;
+  const float* bias = nullptr;
+  const __half* rowbias = nullptr;
+  int ld_rowbias = 0;
+  const __half* residual = nullptr;
+  long long ld_res = 0;
+  void* out = nullptr;
+  long long ld_out = 0;
+  int out_f32 = 0, geglu = 0, act_silu = 0;
+  int bn = 0;  // 0 = choose
+};
+
+struct IgemmOp {
+  IgMaps maps;
+  IgParams p;
+  int bn = 0, grid = 0;
+  double flops = 0;
+};
+
+IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms);
+void igemm_launch(const IgemmOp& op, cudaStream_t s);
+// convenience segment builders
+void seg_conv3x3(IgemmDesc& d, int Cin_total, int C0);           // 9 taps over src0 (C0 ch) [+ src1]
+void seg_conv3x3_s2(IgemmDesc& d, int C, int Nimg, bool vae_pad);  // 9 taps over the 4 parity planes
+void seg_1x1(IgemmDesc& d, int C0, int C1);                       // plain GEMM over src0 [+ src1]
+
+struct AttnDesc {
+  int B = 0, heads = 8, D = 0, Tq = 0, Tk = 0;
+  const __half *q = nullptr, *k = nullptr, *v = nullptr;
+  long long ld_q = 0, ld_k = 0, ld_v = 0;  // token strides (elements)
+  long long bs_q = 0, bs_k = 0, bs_v = 0;  // batch strides (elements)
+  int kv_batches = 0;                      // extent of the K/V batch dim (context slots); 0 = B
+  const int* kv_index = nullptr;
+  __half* out = nullptr;
+  long long ld_out = 0;
+};
+struct AttnOp {
+  AttnMaps maps;
+  AttnParams p;
+  int D = 0;
+  dim3 grid;
+  double flops = 0;
+};
+AttnOp attn_prepare(const AttnDesc& d);
+void attn_launch(const AttnOp& op, cudaStream_t s);
+
+// ---- norm / misc launchers
+struct GnDesc {
+  const __half* src0 = nullptr; int C0 = 0; long long ps0 = 0;
+  const __half* src1 = nullptr; int C1 = 0; long long ps1 = 0;
+  int Nimg = 0, HW = 0;
+  const float *gamma = nullptr, *beta = nullptr;
+  float eps = 1e-5f;
+  int silu = 0;
+  float* partial = nullptr;  // scratch [Nimg * splits * 64]
+  __half* out = nullptr;     // dense [Nimg, HW, C0+C1]
+};
+int gn_splits(int Nimg, int HW);
+void gn_launch(const GnDesc& d, cudaStream_t s);
+void layernorm_launch(const __half* x, long long ld_x, const float* gamma, const float* beta, float eps, long long rows,
+                      int C, __half* out, long long ld_out, cudaStream_t s);
+void patch3x3_launch(const float* x0, const int* x_index, const float* noise, const int* noise_index, const long long* t,
+                     const float* ca, const float* cb, int Bf, int Cin, int H, int W, __half* out, cudaStream_t s);
+void timestep_embed_launch(const long long* t, const int* t_index, int Bf, __half* out, cudaStream_t s);
+void upsample_nearest_launch(const __half* in, int N, int H, int W, int C, int Ho, int Wo, __half* out, cudaStream_t s);
+void space_to_planes_launch(const __half* in, int N, int H, int W, int C, int H2, int W2, __half* out, cudaStream_t s);
+void loss_launch(const __half* pred, int ld_pred, const float* noise, const int* noise_index, const int* grid_row,
+                 float* loss_f32, __half* grid_f16, float* eps_f32, int Bf, int HW, cudaStream_t s);
+void tmap_launch(const __half* grid, int Bi, int N, int n_cond, int HW, float* T, cudaStream_t s);
+void vae_sample_launch(const __half* h16, int ld_h, const __half* wq, const float* bq, const float* eps, float scaling,
+                       int B, int HW, float* z, float* mean_out, float* logvar_out, cudaStream_t s);
+void softmax_rows_launch(const float* S, long long ld_s, int rows, int cols, float scale, __half* P, long long ld_p,
+                         cudaStream_t s);
+void nhwc_to_nchw_mean_launch(const __half* in, int B, int E, int HW, int C, float* out, cudaStream_t s);
+
+}  // namespace dm
