@@ -112,7 +112,10 @@ IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms) {
     kit += d.seg[i].nchunks;
     p.seg[i] = d.seg[i];
   }
-  DM_CHECK(kit * IG_BK == d.K, "igemm: K (" + std::to_string(d.K) + ") != 64 * chunks (" + std::to_string(kit) + ")");
+  if (d.k_ragged)
+    DM_CHECK(kit == (d.K + IG_BK - 1) / IG_BK && d.nseg == 1 && d.K % 8 == 0, "igemm: bad ragged-K description");
+  else
+    DM_CHECK(kit * IG_BK == d.K, "igemm: K (" + std::to_string(d.K) + ") != 64 * chunks (" + std::to_string(kit) + ")");
   p.nseg = d.nseg;
   p.k_iters = kit;
   p.Nimg = d.Nimg; p.H = d.H; p.W = d.W;
@@ -151,7 +154,7 @@ IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms) {
   if (d.nsrc == 1) op.maps.a[1] = op.maps.a[0];
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.N)};
-    const uint64_t st[1] = {static_cast<uint64_t>(d.K) * 2};
+    const uint64_t st[1] = {static_cast<uint64_t>(d.w_ld ? d.w_ld : d.K) * 2};
     const uint32_t box[2] = {64, static_cast<uint32_t>(op.bn)};
     make_tmap(&op.maps.b, d.Wt, 2, dims, st, box);
   }

@@ -43,6 +43,8 @@ struct IgemmDesc {
   IgSeg seg[IG_MAX_SEG];
   const __half* Wt = nullptr;  // [N, K] K-major
   int N = 0, K = 0;
+  long long w_ld = 0;  // weight row stride in elements (0 = K)
+  int k_ragged = 0;    // allow K % 64 != 0: the tail chunk is zero-filled by TMA on both operands
   const float* bias = nullptr;
   const __half* rowbias = nullptr;
   int ld_rowbias = 0;

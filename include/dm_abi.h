@@ -58,6 +58,14 @@ int dm_vae_encode(dm_engine* e, const float* img, const float* eps, int B, int H
 int dm_unet_eps(dm_engine* e, const float* x_noisy, const int64_t* t, const int32_t* ctx_slots, int Bf, int h, int w,
                 float* eps_out, void* stream);
 
+/* General row form of SD.compute_loss (compute.py:95-102): row i uses latent x[x_index[i]], draw
+ * noise[noise_index[i]] with timestep t[noise_index[i]], and context slot ctx_slots[i] (index arrays are HOST
+ * int32 [M]; NULL index = identity).  noise == NULL means x rows are already noisy and t is indexed like x.
+ * loss_out / eps_out (either may be NULL): DEVICE fp32 [M,4,h,w]. */
+int dm_unet_rows(dm_engine* e, const float* x, const float* noise, const int64_t* t, const int32_t* x_index,
+                 const int32_t* noise_index, const int32_t* ctx_slots, int M, int h, int w, float* loss_out,
+                 float* eps_out, int max_forwards, void* stream);
+
 /* replaces SD.compute_loss (compute.py:95-102) for one micro-batch: rows are condition-major
  * [cond0 x S ; cond1 x S ; ...] exactly as D.compute_losses builds them (compute.py:150-152).
  * x0 DEVICE fp32 [1,4,h,w]; noise DEVICE fp32 [S,4,h,w]; t DEVICE int64 [S]; ctx_slots HOST int32 [n_cond];
