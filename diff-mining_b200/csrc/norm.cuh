@@ -15,10 +15,12 @@ struct NormSrc {
   long long pix_stride;  // elements between consecutive pixels
 };
 
-// partial[n][split][g][2] = (sum, sumsq) over this split's pixels; deterministic two-stage reduction.
+// partial[n][split][g][2] = (sum, sumsq) over this split's pixels.  Fully deterministic: per-thread register
+// accumulation over a fixed pixel sequence, then a fixed-order fold through shared memory (no atomics), then a
+// fixed-order sum over splits in gn_apply_kernel -- results are bit-identical run to run and rank to rank.
 __global__ void __launch_bounds__(256) gn_stats_kernel(NormSrc s0, NormSrc s1, int HW, int cpg, int splits,
                                                        float* __restrict__ partial) {
-  __shared__ float gsum[32], gsq[32];
+  __shared__ float sm_a[2048], sm_q[2048];  // [r][local channel] for one pass over <= 256 vector columns
   const int n = blockIdx.y, split = blockIdx.x;
   const int C = s0.C + s1.C;
   const int vcols = C >> 3;
@@ -27,18 +29,18 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(NormSrc s0, NormSrc s1, i
   const int r = threadIdx.x / VT, vt = threadIdx.x % VT;
   const int per = (HW + splits - 1) / splits;
   const int p0 = split * per, p1 = min(HW, p0 + per);
-  if (threadIdx.x < 32) { gsum[threadIdx.x] = 0.f; gsq[threadIdx.x] = 0.f; }
-  __syncthreads();
-  if (r < R) {
-    for (int v = vt; v < vcols; v += VT) {
+  float gs = 0.f, gq = 0.f;  // thread g < 32 owns group g
+  for (int vbase = 0; vbase < vcols; vbase += VT) {
+    const int v = vbase + vt;
+    float a[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = 0.f; q[i] = 0.f; }
+    if (r < R && v < vcols) {
       const int c = v << 3;
       const bool first = c < s0.C;
       const __half* base = first ? s0.ptr + c : s1.ptr + (c - s0.C);
       const long long ps = first ? s0.pix_stride : s1.pix_stride;
       base += static_cast<long long>(n) * HW * ps;
-      float a[8], q[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { a[i] = 0.f; q[i] = 0.f; }
       for (int px = p0 + r; px < p1; px += R) {
         const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + px * ps));
         const __half2* h = reinterpret_cast<const __half2*>(&u);
@@ -49,26 +51,31 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(NormSrc s0, NormSrc s1, i
           a[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
         }
       }
-      // fold the 8 channels into their groups (consecutive channels mostly share one)
-      int g = c / cpg;
-      float sa = 0.f, sq = 0.f;
+    }
+    __syncthreads();  // previous pass fully consumed
+    if (r < R) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int gi = (c + i) / cpg;
-        if (gi != g) {
-          atomicAdd(&gsum[g], sa); atomicAdd(&gsq[g], sq);
-          g = gi; sa = 0.f; sq = 0.f;
-        }
-        sa += a[i]; sq += q[i];
+        sm_a[(r * VT + vt) * 8 + i] = a[i];
+        sm_q[(r * VT + vt) * 8 + i] = q[i];
       }
-      atomicAdd(&gsum[g], sa); atomicAdd(&gsq[g], sq);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      // channels of group g that fall inside this pass: [max(g*cpg, cb), min((g+1)*cpg, ce))
+      const int cb = vbase << 3, ce = min(C, (vbase + VT) << 3);
+      const int lo = max((int)threadIdx.x * cpg, cb), hi = min(((int)threadIdx.x + 1) * cpg, ce);
+      for (int c = lo; c < hi; ++c)
+        for (int rr = 0; rr < R; ++rr) {
+          gs += sm_a[rr * VT * 8 + (c - cb)];
+          gq += sm_q[rr * VT * 8 + (c - cb)];
+        }
     }
   }
-  __syncthreads();
   if (threadIdx.x < 32) {
     float* o = partial + ((static_cast<long long>(n) * splits + split) * 32 + threadIdx.x) * 2;
-    o[0] = gsum[threadIdx.x];
-    o[1] = gsq[threadIdx.x];
+    o[0] = gs;
+    o[1] = gq;
   }
 }
 

@@ -1,0 +1,119 @@
+"""CPU tests of the host-side logic: sharding + the single all-gather (gloo, world_size 2), the reference-surface
+helpers of typicality.D, prompt templating, the T(x|c) reduction."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from diff_mining_b200 import parallel
+from diff_mining_b200 import typicality as ty
+from oracle import sd15
+
+
+def test_shard_indices_round_robin():
+    # compute.py:339 -> lines[i::sub_split]
+    assert parallel.shard_indices(10, 4, 0) == [0, 4, 8]
+    assert parallel.shard_indices(10, 4, 3) == [3, 7]
+    assert parallel.shard_indices(3, 8, 5) == []
+    allidx = sorted(i for r in range(8) for i in parallel.shard_indices(10000, 8, r))
+    assert allidx == list(range(10000))
+
+
+def _gather_worker(rank, world, port, n_total, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        def compute_local(idx):
+            return torch.stack([torch.full((3, 5), float(i)) + torch.arange(5.0) for i in idx]) if idx else torch.zeros(0, 3, 5)
+
+        out = parallel.run_sharded(n_total, compute_local)
+        ref = torch.stack([torch.full((3, 5), float(i)) + torch.arange(5.0) for i in range(n_total)])
+        q.put((rank, bool(torch.equal(out, ref))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [7, 8, 1])
+def test_gather_tmaps_gloo_world2(n_total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + n_total) % 2000
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_schedule_matches_oracle():
+    a, b = ty.scaled_linear_schedule()
+    oa, ob = sd15.schedule_tables()
+    assert torch.equal(a, oa) and torch.equal(b, ob)
+
+
+def test_prompt_templates():
+    # compute.py:41-48
+    assert ty.prompt_for("cars", "1975") == "A car at the 1975's."
+    assert ty.prompt_for("cars", "") == "A car."
+    assert ty.prompt_for("places", "art_gallery") == "Image of art gallery."
+    assert ty.prompt_for("geo", "France") == "France"
+    assert ty.prompt_for("geo", "") == ""
+    assert ty.prompt_for("faces", "") == "Portrait."
+
+
+def test_typicality_map_reduction():
+    # cluster.py:112-123: channel mean -> bilinear -> uncond - cond -> mean over N
+    g = torch.randn(5, 2, 4, 8, 8).abs().half()
+    T = ty.typicality_map(g)
+    ref = (g.float()[:, 1].mean(1) - g.float()[:, 0].mean(1)).mean(0)
+    torch.testing.assert_close(T, ref)
+    T2 = ty.typicality_map(g, size=(64, 64))
+    assert T2.shape == (64, 64)
+    # linear ops commute: upsampling the reduced map equals reducing the upsampled maps
+    up = torch.nn.functional.interpolate(ref[None, None], (64, 64), mode="bilinear")[0, 0]
+    torch.testing.assert_close(T2, up, atol=1e-5, rtol=1e-5)
+
+
+class _FakeSD:
+    device = torch.device("cpu")
+    scheduler = type("S", (), {"num_train_timesteps": 1000})()
+
+
+def test_D_helpers_follow_reference():
+    from PIL import Image
+
+    d = ty.D(_FakeSD(), "/tmp/typ", "cars", seed=42, N=3, t_min=0.1, t_max=0.7)
+    assert d.get_path("/data/cars/1975__a.jpg") == "/tmp/typ/1975__a.npy"     # compute.py:162-163
+    assert d.get_path("x/b.png") == "/tmp/typ/b.npy"
+    img = Image.new("RGB", (640, 480))
+    assert d.rescale(img).size == (341, 256)                                     # compute.py:166-174
+    assert ty.D(_FakeSD(), "", "places").rescale(Image.new("RGB", (300, 600))).size == (512, 1024)
+    x = d.load_image(Image.new("RGB", (16, 8), (255, 0, 127)))
+    assert x.shape == (1, 3, 8, 16) and x[0, 0, 0, 0] == 1.0 and x[0, 1, 0, 0] == -1.0
+    lat = torch.zeros(1, 4, 4, 4)
+    n1, t1 = d.draws(lat)
+    n2, t2 = d.draws(lat)
+    assert n1.shape == (3, 4, 4, 4) and t1.shape == (3,) and t1.dtype == torch.int64
+    assert torch.equal(n1, n2) and torch.equal(t1, t2)          # re-seeded per image (compute.py:139)
+    assert int(t1.min()) >= 100 and int(t1.max()) < 700
+    # identical to the reference's call sequence
+    torch.manual_seed(42)
+    ref = [(torch.randn_like(lat), torch.randint(100, 700, (1,))) for _ in range(3)]
+    assert torch.equal(n1, torch.cat([r[0] for r in ref])) and torch.equal(t1, torch.cat([r[1] for r in ref]))
+
+
+def test_exists_and_call_roundtrip():
+    with tempfile.TemporaryDirectory() as td:
+        d = ty.D(_FakeSD(), td, "geo")
+        assert not d.exists("a/France__1.jpg")
+        arr = np.random.rand(2, 2, 4, 3, 3).astype(np.float16)
+        np.save(open(d.get_path("a/France__1.jpg"), "wb"), arr)
+        assert d.exists("a/France__1.jpg")
+        np.testing.assert_array_equal(d("a/France__1.jpg"), arr)
