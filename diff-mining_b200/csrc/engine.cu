@@ -346,7 +346,7 @@ void Engine::finalize() {
     }
   }
   staging.clear();
-  gn_partial_floats = 64ull * (592 + 8192);
+  gn_partial_floats = 64ull * 64 * 8192;  // 64 floats x <=64 splits x <=8192 images
   gn_partial = static_cast<float*>(dmalloc(gn_partial_floats * sizeof(float)));
   if (!sched_a) {
     // default SD-1.5 schedule (scaled_linear 0.00085 -> 0.012, 1000 steps) until dm_set_schedule overrides it

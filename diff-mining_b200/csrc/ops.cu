@@ -241,9 +241,10 @@ static int grid_for(long long total, int block = 256, int cap = 148 * 16) {
 }
 
 int gn_splits(int Nimg, int HW) {
-  int s = std::max(1, (148 * 4 + Nimg - 1) / Nimg);
-  s = std::min(s, std::max(1, HW / 16));
-  return std::min(s, 64);
+  // depends on HW only: the partial-sum grouping (hence every output bit) must not change with the batch size,
+  // so an image scores identically alone, inside any micro-batch, and on any rank
+  (void)Nimg;
+  return std::min(64, std::max(1, HW / 256));
 }
 
 void gn_launch(const GnDesc& d, cudaStream_t s) {
