@@ -1,0 +1,78 @@
+"""Profiling targets for ncu (run under gpurun; see profiles/README.md).
+  python tools/profile_target.py unet   -> one 32-forward U-Net micro-batch @64x64 between cudaProfilerStart/Stop
+                                           (eager replay, DM_GRAPH=0), preceded by an identical warm-up
+  python tools/profile_target.py ops    -> the three dominant kernel shapes launched alone through the op-level ABI
+"""
+import ctypes
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("DM_GRAPH", "0")
+
+
+def unet():
+    from diff_mining_b200.engine import Engine
+    from oracle import sd15
+
+    usd = sd15.make_synthetic_weights(sd15.unet_param_shapes(), seed=0)
+    eng = Engine(0)
+    eng.load_state_dict(usd, "unet.")
+    eng.finalize()
+    g = torch.Generator().manual_seed(5)
+    for i in range(2):
+        eng.set_context(i, torch.randn(77, 768, generator=g))
+    Bf = int(os.environ.get("DM_BF", "32"))
+    x = torch.randn(Bf, 4, 64, 64, generator=g).cuda()
+    t = torch.randint(100, 700, (Bf,), generator=g).cuda()
+    slots = [i % 2 for i in range(Bf)]
+    for _ in range(2):
+        eng.unet_eps(x, t, slots)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
+    eng.unet_eps(x, t, slots)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+
+
+def ops():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gpu_optest as o
+
+    lib, ptr, stream = o.lib, o.ptr, o.stream
+
+    def conv(N, H, W, C0, Cout, ks, geglu=0, res=False):
+        x = torch.randn(N, H, W, C0, device="cuda").half()
+        w = (torch.randn(Cout, ks * ks * C0, device="cuda") / (ks * ks * C0) ** 0.5).half()
+        b = torch.randn(Cout, device="cuda")
+        r = torch.randn(N * H * W, Cout, device="cuda").half() if res else None
+        out = torch.empty(N * H * W, Cout // 2 if geglu else Cout, device="cuda", dtype=torch.float16)
+        return lambda: o.check(lib.dm_op_conv(ptr(x), None, N, H, W, C0, 0, ptr(w), Cout, ks, 1, 0, ptr(b), None, ptr(r), ptr(out), 0, geglu, 0, 0, stream())), (x, w, b, r, out)
+
+    def attn(B, T, D):
+        C = 8 * D
+        qkv = torch.randn(B, T, 3 * C, device="cuda").half()
+        out = torch.empty(B, T, C, device="cuda", dtype=torch.float16)
+        args = (ptr(qkv[..., :C]), ptr(qkv[..., C:2 * C]), ptr(qkv[..., 2 * C:]), 3 * C, 3 * C, 3 * C, T * 3 * C, T * 3 * C, T * 3 * C, B, 8, D, T, T, 0, None, ptr(out), C, stream())
+        return lambda: o.check(lib.dm_op_attention(*args)), (qkv, out)
+
+    targets = [conv(32, 64, 64, 320, 320, 3), conv(32, 64, 64, 320, 2560, 1, geglu=1), conv(32, 64, 64, 320, 320, 1, res=True),
+               conv(32, 16, 16, 1280, 1280, 3), attn(32, 4096, 40), attn(32, 1024, 80)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for f, _ in targets:
+        for _ in range(2):
+            f()
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
+    for f, _ in targets:
+        flush.zero_()
+        f()
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+
+
+if __name__ == "__main__":
+    {"unet": unet, "ops": ops}[sys.argv[1]]()
