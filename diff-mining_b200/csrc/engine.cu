@@ -348,6 +348,11 @@ void Engine::finalize() {
   staging.clear();
   gn_partial_floats = 64ull * 64 * 8192;  // 64 floats x <=64 splits x <=8192 images
   gn_partial = static_cast<float*>(dmalloc(gn_partial_floats * sizeof(float)));
+  gn_ab_floats = 8ull << 20;  // 2 floats x (images x channels) <= 4 Mi entries
+  gn_ab = static_cast<float*>(dmalloc(gn_ab_floats * sizeof(float)));
+  gn_ticket_count = 8192;
+  gn_tickets = static_cast<unsigned*>(dmalloc(gn_ticket_count * sizeof(unsigned)));
+  DM_CUDA(cudaMemset(gn_tickets, 0, gn_ticket_count * sizeof(unsigned)));
   if (!sched_a) {
     // default SD-1.5 schedule (scaled_linear 0.00085 -> 0.012, 1000 steps) until dm_set_schedule overrides it
     std::vector<float> a(1000), b(1000);

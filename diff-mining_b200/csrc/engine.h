@@ -106,6 +106,10 @@ struct Engine {
   Plan* last_unet_plan = nullptr;
   float* gn_partial = nullptr;  // shared GroupNorm scratch
   size_t gn_partial_floats = 0;
+  float* gn_ab = nullptr;          // GroupNorm per-(image, channel) scale/shift scratch
+  size_t gn_ab_floats = 0;
+  unsigned* gn_tickets = nullptr;  // GroupNorm last-block tickets (always left zero)
+  size_t gn_ticket_count = 0;
   cudaStream_t cap_stream = nullptr;
   int64_t launch_count = 0;
   double flop_count = 0;

@@ -1,9 +1,10 @@
-// GroupNorm(32 groups)(+SiLU) and LayerNorm over NHWC fp16 activations.  HBM-bound passes:
-// 16-byte vector loads/stores, fp32 statistics, one rounding to fp16 at the end -- the same rounding
-// point torch.autocast gives the reference (group_norm / layer_norm run in fp32 and their fp32 output is
-// cast to fp16 by the next conv / Linear).  GroupNorm reads up to two source tensors so the up-blocks'
-// cat(hidden, skip) (reference: /root/reference/diffmining/typicality/dift.py:141-165) is never materialised
-// un-normalised; groups may straddle the concat boundary.
+// GroupNorm(32 groups)(+SiLU) and LayerNorm over NHWC fp16 activations.  HBM-bound streaming passes:
+// every thread owns one fixed 16-byte channel vector and walks pixel rows with four independent loads in
+// flight; fp32 statistics, one rounding to fp16 at the end -- the same rounding point torch.autocast gives
+// the reference (group_norm / layer_norm run in fp32 and their fp32 output is cast to fp16 by the next
+// conv / Linear).  GroupNorm reads up to two source tensors so the up-blocks' cat(hidden, skip)
+// (reference: /root/reference/diffmining/typicality/dift.py:141-165) is never materialised un-normalised;
+// groups may straddle the concat boundary.
 #pragma once
 #include "ptx.cuh"
 
@@ -15,177 +16,250 @@ struct NormSrc {
   long long pix_stride;  // elements between consecutive pixels
 };
 
-// partial[n][split][g][2] = (sum, sumsq) over this split's pixels.  Fully deterministic: per-thread register
-// accumulation over a fixed pixel sequence, then a fixed-order fold through shared memory (no atomics), then a
-// fixed-order sum over splits in gn_apply_kernel -- results are bit-identical run to run and rank to rank.
-__global__ void __launch_bounds__(256) gn_stats_kernel(NormSrc s0, NormSrc s1, int HW, int cpg, int splits,
-                                                       float* __restrict__ partial) {
-  __shared__ float sm_a[2048], sm_q[2048];  // [r][local channel] for one pass over <= 256 vector columns
-  const int n = blockIdx.y, split = blockIdx.x;
-  const int C = s0.C + s1.C;
-  const int vcols = C >> 3;
-  const int VT = vcols < (int)blockDim.x ? vcols : (int)blockDim.x;  // vector columns handled concurrently
-  const int R = blockDim.x / VT;                                      // pixel rows in flight
-  const int r = threadIdx.x / VT, vt = threadIdx.x % VT;
-  const int per = (HW + splits - 1) / splits;
-  const int p0 = split * per, p1 = min(HW, p0 + per);
-  float gs = 0.f, gq = 0.f;  // thread g < 32 owns group g
-  for (int vbase = 0; vbase < vcols; vbase += VT) {
-    const int v = vbase + vt;
-    float a[8], q[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { a[i] = 0.f; q[i] = 0.f; }
-    if (r < R && v < vcols) {
-      const int c = v << 3;
-      const bool first = c < s0.C;
-      const __half* base = first ? s0.ptr + c : s1.ptr + (c - s0.C);
-      const long long ps = first ? s0.pix_stride : s1.pix_stride;
-      base += static_cast<long long>(n) * HW * ps;
-      for (int px = p0 + r; px < p1; px += R) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + px * ps));
-        const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __half22float2(h[i]);
-          a[2 * i] += f.x; q[2 * i] += f.x * f.x;
-          a[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
-        }
-      }
-    }
-    __syncthreads();  // previous pass fully consumed
-    if (r < R) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        sm_a[(r * VT + vt) * 8 + i] = a[i];
-        sm_q[(r * VT + vt) * 8 + i] = q[i];
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      // channels of group g that fall inside this pass: [max(g*cpg, cb), min((g+1)*cpg, ce))
-      const int cb = vbase << 3, ce = min(C, (vbase + VT) << 3);
-      const int lo = max((int)threadIdx.x * cpg, cb), hi = min(((int)threadIdx.x + 1) * cpg, ce);
-      for (int c = lo; c < hi; ++c)
-        for (int rr = 0; rr < R; ++rr) {
-          gs += sm_a[rr * VT * 8 + (c - cb)];
-          gq += sm_q[rr * VT * 8 + (c - cb)];
-        }
-    }
-  }
-  if (threadIdx.x < 32) {
-    float* o = partial + ((static_cast<long long>(n) * splits + split) * 32 + threadIdx.x) * 2;
-    o[0] = gs;
-    o[1] = gq;
-  }
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+
+__device__ __forceinline__ const __half* norm_src_ptr(const NormSrc& s0, const NormSrc& s1, int c, long long& ps) {
+  const bool first = c < s0.C;
+  ps = first ? s0.pix_stride : s1.pix_stride;
+  return first ? s0.ptr + c : s1.ptr + (c - s0.C);
 }
 
-// y = (x - mean) * rstd * gamma + beta (+SiLU) -> dense NHWC fp16 [Nimg, HW, C]
-__global__ void __launch_bounds__(256) gn_apply_kernel(NormSrc s0, NormSrc s1, int HW, int cpg, int splits,
-                                                       const float* __restrict__ partial,
-                                                       const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, float eps, int silu,
-                                                       int chunks, __half* __restrict__ out) {
-  extern __shared__ float2 ab[];  // [C] (scale, shift)
-  __shared__ float mean_s[32], rstd_s[32];
-  const int n = blockIdx.y;
+// Pass 1.  grid (splits, Nimg), block >= max(256, VT*R) threads: thread (r, vt), r < R, owns channel vector vt and pixels
+// p0+r, p0+r+R, ... of this split.  partial[n][split][g] = (sum, sumsq); the LAST block of an image
+// (atomic ticket) folds the splits in index order and writes the per-(image, channel) affine
+// ab[n][c] = (gamma*rstd, beta - mean*gamma*rstd).  Deterministic: fixed per-thread pixel sequence, fixed
+// shared-memory fold, fixed split order -- no floating-point atomics; the ticket only elects who folds.
+// The split geometry depends on (HW, C) alone, so an image's statistics do not depend on the batch it is in.
+__global__ void __launch_bounds__(384) gn_stats_kernel(NormSrc s0, NormSrc s1, int HW, int cpg, int splits, int px_per,
+                                                        int VT, int R, float* __restrict__ partial,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps, float2* __restrict__ ab, unsigned* __restrict__ tickets) {
+  extern __shared__ float sm_gn[];  // [2][R*VT*8] per-thread channel sums, later mean/rstd
+  __shared__ int is_last;
+  const int n = blockIdx.y, split = blockIdx.x;
   const int C = s0.C + s1.C;
+  const int nthr = VT * R;
+  float* sm_a = sm_gn;
+  float* sm_q = sm_gn + nthr * 8;
+  const int r = threadIdx.x / VT, vt = threadIdx.x % VT;
+  const int p0 = split * px_per, p1 = min(HW, p0 + px_per);
+  float a[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a[i] = 0.f; q[i] = 0.f; }
+  const bool active = threadIdx.x < nthr;
+  if (active) {
+    long long ps;
+    const __half* base = norm_src_ptr(s0, s1, vt << 3, ps);
+    base += static_cast<long long>(n) * HW * ps;
+    auto acc = [&](const uint4& u) {
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        a[2 * i] += f.x; q[2 * i] += f.x * f.x;
+        a[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+      }
+    };
+    int px = p0 + r;
+    for (; px + 3 * R < p1; px += 4 * R) {
+      const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(base + px * ps));
+      const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(base + (px + R) * ps));
+      const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(base + (px + 2 * R) * ps));
+      const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(base + (px + 3 * R) * ps));
+      acc(u0); acc(u1); acc(u2); acc(u3);
+    }
+    for (; px < p1; px += R) acc(__ldg(reinterpret_cast<const uint4*>(base + px * ps)));
+  }
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sm_a[threadIdx.x * 8 + i] = a[i];  // index = (r*VT + vt)*8 + i = r*C + channel
+      sm_q[threadIdx.x * 8 + i] = q[i];
+    }
+  }
+  __syncthreads();
+  {
+    // group g folded by 8 consecutive lanes (k = lane & 7), then a fixed xor tree
+    const int g = threadIdx.x >> 3, k = threadIdx.x & 7;
+    float gs = 0.f, gq = 0.f;
+    if (g < 32) {
+      for (int rr = 0; rr < R; ++rr)
+        for (int cc = k; cc < cpg; cc += 8) {
+          gs += sm_a[rr * C + g * cpg + cc];
+          gq += sm_q[rr * C + g * cpg + cc];
+        }
+    }
+    if (threadIdx.x < 256) {  // whole warps (blockDim >= 256 is guaranteed by the launcher)
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        gs += __shfl_xor_sync(0xffffffffu, gs, o);
+        gq += __shfl_xor_sync(0xffffffffu, gq, o);
+      }
+      if (k == 0) {
+        float* o = partial + ((static_cast<long long>(n) * splits + split) * 32 + g) * 2;
+        o[0] = gs;
+        o[1] = gq;
+      }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(&tickets[n], 1u) == static_cast<unsigned>(splits - 1));
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float* mean_s = sm_gn;
+  float* rstd_s = sm_gn + 32;
   if (threadIdx.x < 32) {
-    float s = 0.f, q = 0.f;
+    float s = 0.f, qq = 0.f;
     const float* pp = partial + (static_cast<long long>(n) * splits * 32 + threadIdx.x) * 2;
-    for (int i = 0; i < splits; ++i) { s += pp[i * 64]; q += pp[i * 64 + 1]; }
+    for (int i = 0; i < splits; ++i) {
+      s += __ldcg(pp + i * 64);
+      qq += __ldcg(pp + i * 64 + 1);
+    }
     const float cnt = static_cast<float>(HW) * cpg;
     const float mean = s / cnt;
-    const float var = fmaxf(q / cnt - mean * mean, 0.f);
+    const float var = fmaxf(qq / cnt - mean * mean, 0.f);
     mean_s[threadIdx.x] = mean;
     rstd_s[threadIdx.x] = rsqrtf(var + eps);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
-    const float a = gamma[c] * rstd_s[g];
-    ab[c] = make_float2(a, beta[c] - mean_s[g] * a);
+    const float sc = gamma[c] * rstd_s[g];
+    ab[static_cast<long long>(n) * C + c] = make_float2(sc, beta[c] - mean_s[g] * sc);
   }
-  __syncthreads();
-  const int vcols = C >> 3;
-  const int per = (HW + chunks - 1) / chunks;
-  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
-  const long long total = static_cast<long long>(p1 - p0) * vcols;
-  for (long long idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int px = p0 + static_cast<int>(idx / vcols);
-    const int c = static_cast<int>(idx % vcols) << 3;
-    const bool first = c < s0.C;
-    const __half* src = first ? s0.ptr + (static_cast<long long>(n) * HW + px) * s0.pix_stride + c
-                              : s1.ptr + (static_cast<long long>(n) * HW + px) * s1.pix_stride + (c - s0.C);
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
+  if (threadIdx.x == 0) tickets[n] = 0;  // self-cleaning for the next GroupNorm on this stream
+}
+
+// Pass 2.  y = x * a + b (+SiLU) -> dense NHWC fp16 [Nimg, HW, C]; grid (pixel blocks, Nimg), same thread map.
+__global__ void __launch_bounds__(384) gn_apply_kernel(NormSrc s0, NormSrc s1, int HW, int px_per, int VT, int R,
+                                                        const float2* __restrict__ ab, int silu,
+                                                        __half* __restrict__ out) {
+  const int n = blockIdx.y;
+  const int C = s0.C + s1.C;
+  if (threadIdx.x >= VT * R) return;
+  const int r = threadIdx.x / VT, vt = threadIdx.x % VT;
+  const int c = vt << 3;
+  const int p0 = blockIdx.x * px_per, p1 = min(HW, p0 + px_per);
+  float sa[8], sb[8];
+  {
+    const float4* p = reinterpret_cast<const float4*>(ab + static_cast<long long>(n) * C + c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 f = p[i];
+      sa[2 * i] = f.x; sb[2 * i] = f.y; sa[2 * i + 1] = f.z; sb[2 * i + 1] = f.w;
+    }
+  }
+  long long ps;
+  const __half* base = norm_src_ptr(s0, s1, c, ps);
+  base += static_cast<long long>(n) * HW * ps;
+  __half* obase = out + static_cast<long long>(n) * HW * C + c;
+  auto apply = [&](const uint4& u, int px) {
     const __half2* h = reinterpret_cast<const __half2*>(&u);
     uint32_t pk[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float2 f = __half22float2(h[i]);
-      const float2 ab0 = ab[c + 2 * i], ab1 = ab[c + 2 * i + 1];
-      float y0 = f.x * ab0.x + ab0.y, y1 = f.y * ab1.x + ab1.y;
-      if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+      float y0 = f.x * sa[2 * i] + sb[2 * i], y1 = f.y * sa[2 * i + 1] + sb[2 * i + 1];
+      if (silu) { y0 = silu_fast(y0); y1 = silu_fast(y1); }
       pk[i] = pack_h2(y0, y1);
     }
-    *reinterpret_cast<uint4*>(out + (static_cast<long long>(n) * HW + px) * C + c) =
-        make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(obase + static_cast<long long>(px) * C) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  };
+  int px = p0 + r;
+  for (; px + 3 * R < p1; px += 4 * R) {
+    const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(base + px * ps));
+    const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(base + (px + R) * ps));
+    const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(base + (px + 2 * R) * ps));
+    const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(base + (px + 3 * R) * ps));
+    apply(u0, px); apply(u1, px + R); apply(u2, px + 2 * R); apply(u3, px + 3 * R);
   }
+  for (; px < p1; px += R) apply(__ldg(reinterpret_cast<const uint4*>(base + px * ps)), px);
 }
 
-// LayerNorm over the last dim (C <= 1280, multiple of 8); one warp per token.
+// LayerNorm over the last dim (C <= 32*8*MAXV, multiple of 8).  Persistent warps: a warp walks rows
+// w, w+W, ... holding one row in registers while the next row's loads are already in flight; gamma / beta
+// live in registers as packed halves (they are fp16 values).
+template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, long long ld_x,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, long long rows,
                                                         int C, __half* __restrict__ out, long long ld_out) {
-  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int lane = threadIdx.x & 31;
+  const long long nw = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int vcols = C >> 3;
-  constexpr int MAXV = 5;
-  float v[MAXV][8];
-  float s = 0.f;
+  uint32_t gp[MAXV][4], bp[MAXV][4];
 #pragma unroll
   for (int k = 0; k < MAXV; ++k) {
     const int vc = lane + 32 * k;
-    if (vc < vcols) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + row * ld_x + (vc << 3)));
-      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      gp[k][i] = 0; bp[k][i] = 0;
+      if (vc < vcols) {
+        gp[k][i] = pack_h2(gamma[(vc << 3) + 2 * i], gamma[(vc << 3) + 2 * i + 1]);
+        bp[k][i] = pack_h2(beta[(vc << 3) + 2 * i], beta[(vc << 3) + 2 * i + 1]);
+      }
+    }
+  }
+  uint4 cur[MAXV], nxt[MAXV];
+  auto load = [&](uint4* dst, long long rw) {
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int vc = lane + 32 * k;
+      dst[k] = make_uint4(0, 0, 0, 0);
+      if (vc < vcols) dst[k] = __ldg(reinterpret_cast<const uint4*>(x + rw * ld_x + (vc << 3)));
+    }
+  };
+  if (row < rows) load(cur, row);
+  const float invC = 1.f / static_cast<float>(C);
+  while (row < rows) {
+    const long long nrow = row + nw;
+    if (nrow < rows) load(nxt, nrow);
+    float v[MAXV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const __half2* h = reinterpret_cast<const __half2*>(&cur[k]);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 f = __half22float2(h[i]);
         v[k][2 * i] = f.x; v[k][2 * i + 1] = f.y;
-        s += f.x + f.y;
+        s += f.x + f.y;  // lanes past vcols hold zeros
       }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / C;
-  float q = 0.f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * invC;
+    float q = 0.f;
 #pragma unroll
-  for (int k = 0; k < MAXV; ++k) {
-    if (lane + 32 * k < vcols) {
+    for (int k = 0; k < MAXV; ++k) {
+      if (lane + 32 * k < vcols) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { const float d = v[k][i] - mean; q += d * d; }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / C + eps);
-#pragma unroll
-  for (int k = 0; k < MAXV; ++k) {
-    const int vc = lane + 32 * k;
-    if (vc < vcols) {
-      const int c = vc << 3;
-      uint32_t pk[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float y0 = (v[k][2 * i] - mean) * rstd * gamma[c + 2 * i] + beta[c + 2 * i];
-        const float y1 = (v[k][2 * i + 1] - mean) * rstd * gamma[c + 2 * i + 1] + beta[c + 2 * i + 1];
-        pk[i] = pack_h2(y0, y1);
+        for (int i = 0; i < 8; ++i) { const float d = v[k][i] - mean; q += d * d; }
       }
-      *reinterpret_cast<uint4*>(out + row * ld_out + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * invC + eps);
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int vc = lane + 32 * k;
+      if (vc < vcols) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 g = __half22float2(*reinterpret_cast<const __half2*>(&gp[k][i]));
+          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&bp[k][i]));
+          pk[i] = pack_h2((v[k][2 * i] - mean) * rstd * g.x + b.x, (v[k][2 * i + 1] - mean) * rstd * g.y + b.y);
+        }
+        *reinterpret_cast<uint4*>(out + row * ld_out + (vc << 3)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) cur[k] = nxt[k];
+    row = nrow;
   }
 }
 

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -193,6 +194,10 @@ AttnOp attn_prepare(const AttnDesc& d) {
   DM_CHECK(d.D == 40 || d.D == 80 || d.D == 160, "attention: head_dim must be 40, 80 or 160");
   DM_CHECK(d.Tq > 0 && d.Tk > 0 && d.B > 0, "attention: empty problem");
   op.D = d.D;
+  // long self-attention (head_dim 40 / 80) -> warp-specialised kernel; short key sets (cross-attention, 77 keys)
+  // and head_dim 160 stay on the one-tile kernel.  DM_ATTN2=0 disables, DM_ATTN2=2 also routes cross-attention.
+  static const int attn2_mode = [] { const char* e = getenv("DM_ATTN2"); return e ? atoi(e) : 1; }();
+  op.v2 = (d.D == 40 || d.D == 80) && attn2_mode > 0 && (d.Tk > 128 || attn2_mode > 1) ? 1 : 0;
   const int bkv = d.D == 40 ? 128 : 64;
   auto mk = [&](CUtensorMap* m, const __half* ptr, long long ld, long long bs, int T, int nb, int rows) {
     const uint64_t dims[4] = {static_cast<uint64_t>(d.D), static_cast<uint64_t>(d.heads), static_cast<uint64_t>(T),
@@ -209,7 +214,7 @@ AttnOp attn_prepare(const AttnDesc& d) {
   op.p.kv_index = d.kv_index;
   op.p.out = d.out; op.p.ld_out = d.ld_out;
   op.p.scale_log2 = static_cast<float>(1.0 / std::sqrt(static_cast<double>(d.D)) * 1.4426950408889634);
-  op.grid = dim3((d.Tq + 127) / 128, d.heads, d.B);
+  op.grid = op.v2 ? dim3((d.Tq + 255) / 256, d.heads, d.B) : dim3((d.Tq + 127) / 128, d.heads, d.B);
   op.flops = 4.0 * d.B * d.heads * static_cast<double>(d.Tq) * d.Tk * d.D;
   return op;
 }
@@ -225,7 +230,23 @@ static void attn_launch_d(const AttnOp& op, cudaStream_t s) {
   attention_kernel<D, BKV><<<op.grid, 128, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
   DM_CUDA(cudaGetLastError());
 }
+template <int D, int BKV, int ST>
+static void attn2_launch_d(const AttnOp& op, cudaStream_t s) {
+  static bool configured = false;
+  using Cfg = Attn2Cfg<D, BKV, ST>;
+  if (!configured) {
+    DM_CUDA(cudaFuncSetAttribute(attention2_kernel<D, BKV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  attention2_kernel<D, BKV, ST><<<op.grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
+  DM_CUDA(cudaGetLastError());
+}
 void attn_launch(const AttnOp& op, cudaStream_t s) {
+  if (op.v2) {
+    if (op.D == 40) attn2_launch_d<40, 128, 2>(op, s);
+    else attn2_launch_d<80, 64, 3>(op, s);
+    return;
+  }
   switch (op.D) {
     case 40: attn_launch_d<40, 128>(op, s); break;
     case 80: attn_launch_d<80, 64>(op, s); break;
@@ -240,36 +261,57 @@ static int grid_for(long long total, int block = 256, int cap = 148 * 16) {
   return static_cast<int>(std::max<long long>(1, std::min<long long>(g, cap)));
 }
 
+struct GnGeom {
+  int VT, R, threads, px_stats, splits, px_apply, blocks_apply;
+};
+// The geometry depends on (HW, C) only: the partial-sum grouping (hence every output bit) must not change with the
+// batch size, so an image scores identically alone, inside any micro-batch, and on any rank.
+static GnGeom gn_geom(int HW, int C) {
+  GnGeom g;
+  g.VT = C / 8;
+  g.R = std::max(1, 384 / g.VT);
+  g.threads = std::max(256, (g.VT * g.R + 31) / 32 * 32);
+  g.px_stats = std::min(64, std::max(16, HW / 16));
+  if ((HW + g.px_stats - 1) / g.px_stats > 64) g.px_stats = (HW + 63) / 64;
+  g.splits = (HW + g.px_stats - 1) / g.px_stats;
+  g.px_apply = std::min(128, std::max(16, HW / 16));
+  g.blocks_apply = (HW + g.px_apply - 1) / g.px_apply;
+  return g;
+}
 int gn_splits(int Nimg, int HW) {
-  // depends on HW only: the partial-sum grouping (hence every output bit) must not change with the batch size,
-  // so an image scores identically alone, inside any micro-batch, and on any rank
   (void)Nimg;
-  return std::min(64, std::max(1, HW / 256));
+  return gn_geom(HW, 320).splits;  // C does not enter the split count
 }
 
 void gn_launch(const GnDesc& d, cudaStream_t s) {
   const int C = d.C0 + d.C1;
   DM_CHECK(C % 32 == 0 && d.C0 % 8 == 0 && d.C1 % 8 == 0, "groupnorm: channel counts must be multiples of 8 / 32");
+  DM_CHECK(C <= 3072, "groupnorm: more than 3072 channels");
+  DM_CHECK(d.Nimg <= 65535, "groupnorm: more than 65535 images in one call");
+  DM_CHECK(d.partial && d.ab && d.tickets, "groupnorm: missing scratch");
   const int cpg = C / 32;
-  const int splits = gn_splits(d.Nimg, d.HW);
+  const GnGeom g = gn_geom(d.HW, C);
   NormSrc s0{d.src0, d.C0, d.ps0}, s1{d.src1, d.C1, d.ps1};
-  const int vcols = C / 8;
-  const int threads = vcols <= 256 ? vcols * (256 / vcols) : 256;
-  gn_stats_kernel<<<dim3(splits, d.Nimg), threads, 0, s>>>(s0, s1, d.HW, cpg, splits, d.partial);
+  const size_t smem = static_cast<size_t>(g.VT) * g.R * 8 * 2 * sizeof(float);
+  gn_stats_kernel<<<dim3(g.splits, d.Nimg), g.threads, std::max<size_t>(smem, 256), s>>>(
+      s0, s1, d.HW, cpg, g.splits, g.px_stats, g.VT, g.R, d.partial, d.gamma, d.beta, d.eps,
+      reinterpret_cast<float2*>(d.ab), d.tickets);
   DM_CUDA(cudaGetLastError());
-  const long long per_img = static_cast<long long>(d.HW) * vcols;
-  int chunks = static_cast<int>(std::min<long long>(std::max<long long>(1, per_img / 2048), 1024));
-  chunks = std::min(chunks, d.HW);
-  gn_apply_kernel<<<dim3(chunks, d.Nimg), 256, C * sizeof(float2), s>>>(s0, s1, d.HW, cpg, splits, d.partial, d.gamma,
-                                                                        d.beta, d.eps, d.silu, chunks, d.out);
+  gn_apply_kernel<<<dim3(g.blocks_apply, d.Nimg), g.threads, 0, s>>>(s0, s1, d.HW, g.px_apply, g.VT, g.R,
+                                                                    reinterpret_cast<const float2*>(d.ab), d.silu, d.out);
   DM_CUDA(cudaGetLastError());
 }
 
 void layernorm_launch(const __half* x, long long ld_x, const float* gamma, const float* beta, float eps, long long rows,
                       int C, __half* out, long long ld_out, cudaStream_t s) {
   DM_CHECK(C % 8 == 0 && C <= 1280, "layernorm: C must be a multiple of 8 and <= 1280");
-  const long long blocks = (rows + 7) / 8;
-  layernorm_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(x, ld_x, gamma, beta, eps, rows, C, out, ld_out);
+  // persistent warps: 8 per block, enough blocks to fill the machine (148 SMs x 8 resident blocks)
+  const long long want = (rows + 7) / 8;
+  const unsigned blocks = static_cast<unsigned>(std::max<long long>(1, std::min<long long>(want, 148 * 8)));
+  const int maxv = (C / 8 + 31) / 32;
+  if (maxv <= 2) layernorm_kernel<2><<<blocks, 256, 0, s>>>(x, ld_x, gamma, beta, eps, rows, C, out, ld_out);
+  else if (maxv == 3) layernorm_kernel<3><<<blocks, 256, 0, s>>>(x, ld_x, gamma, beta, eps, rows, C, out, ld_out);
+  else layernorm_kernel<5><<<blocks, 256, 0, s>>>(x, ld_x, gamma, beta, eps, rows, C, out, ld_out);
   DM_CUDA(cudaGetLastError());
 }
 

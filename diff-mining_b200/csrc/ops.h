@@ -8,7 +8,7 @@
 #include <stdexcept>
 #include <string>
 
-#include "attention.cuh"
+#include "attention2.cuh"
 #include "igemm.cuh"
 
 namespace dm {
@@ -84,6 +84,7 @@ struct AttnOp {
   AttnMaps maps;
   AttnParams p;
   int D = 0;
+  int v2 = 0;  // 1 = warp-specialised two-Q-tile kernel (attention2.cuh)
   dim3 grid;
   double flops = 0;
 };
@@ -99,6 +100,8 @@ struct GnDesc {
   float eps = 1e-5f;
   int silu = 0;
   float* partial = nullptr;  // scratch [Nimg * splits * 64]
+  float* ab = nullptr;       // scratch [Nimg * C * 2]: per-(image, channel) scale / shift
+  unsigned* tickets = nullptr;  // scratch [Nimg], zero on entry, left zero
   __half* out = nullptr;     // dense [Nimg, HW, C0+C1]
 };
 int gn_splits(int Nimg, int HW);

@@ -44,19 +44,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.  The slow path is kept out of
+// line (and printf only with -DDM_WAIT_DEBUG) so hot loops do not pay for the call's register constraints.
 #ifndef DM_WAIT_LIMIT_CYCLES
 #define DM_WAIT_LIMIT_CYCLES (6000000000ll)
 #endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (ok) return;
     if (clock64() - t0 > DM_WAIT_LIMIT_CYCLES) {
+#ifdef DM_WAIT_DEBUG
       printf("dm: mbarrier wait timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+#endif
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(smem_u32(bar), parity);
 }
 
 // ------------------------------------------------------------------ TMA loads (tile mode)

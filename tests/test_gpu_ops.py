@@ -183,12 +183,13 @@ def test_groupnorm_silu(lib, case):
     assert torch.equal(out, out2)  # deterministic reduction: bit-identical run to run
 
 
-@pytest.mark.parametrize("rows,C", [(4096, 320), (1000, 640), (77, 1280), (1, 320)])
+@pytest.mark.parametrize("rows,C", [(4096, 320), (1000, 640), (77, 1280), (1, 320), (40000, 320), (20001, 1280), (300, 512)])
 def test_layernorm(lib, rows, C):
     g = torch.Generator(device="cuda").manual_seed(11 + rows)
     x = (torch.randn(rows, C, device="cuda", generator=g) * 2 + 0.5).half()
-    gamma = torch.randn(C, device="cuda", generator=g)
-    beta = torch.randn(C, device="cuda", generator=g)
+    # the kernel keeps gamma / beta as packed halves: in the engine they ARE fp16 weights (stored as fp32 copies)
+    gamma = torch.randn(C, device="cuda", generator=g).half().float()
+    beta = torch.randn(C, device="cuda", generator=g).half().float()
     out = torch.full((rows, C), float("nan"), device="cuda", dtype=torch.float16)
     check(lib, lib.dm_op_layernorm(ptr(x), rows, C, ptr(gamma), ptr(beta), 1e-5, ptr(out), stream()))
     ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)

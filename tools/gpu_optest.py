@@ -182,6 +182,9 @@ def attn_cases():
     ok &= attn_case(2, 256, 256, 160)
     ok &= attn_case(3, 64, 64, 160)
     ok &= attn_case(2, 1000, 1000, 40)
+    ok &= attn_case(1, 300, 300, 80)
+    ok &= attn_case(3, 257, 257, 40)
+    ok &= attn_case(1, 129, 129, 40)
     ok &= attn_case(4, 4096, 77, 40, cross=True)
     ok &= attn_case(4, 1024, 77, 80, cross=True)
     ok &= attn_case(4, 256, 77, 160, cross=True)
@@ -229,6 +232,36 @@ def bench_conv():
         print(f"BENCH attn B{B} T{T} D{D}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s", flush=True)
 
 
+def bench_attn():
+    """event-timed attention shapes of one 32-forward micro-batch (self + cross)"""
+    for (B, T, Tk, D) in [(32, 4096, 4096, 40), (32, 1024, 1024, 80), (32, 256, 256, 160), (32, 4096, 77, 40), (32, 1024, 77, 80)]:
+        C = 8 * D
+        if Tk == T:
+            qkv = torch.randn(B, T, 3 * C, device="cuda").half()
+            out = torch.empty(B, T, C, device="cuda", dtype=torch.float16)
+            args = (ptr(qkv[..., :C]), ptr(qkv[..., C:2 * C]), ptr(qkv[..., 2 * C:]), 3 * C, 3 * C, 3 * C, T * 3 * C, T * 3 * C,
+                    T * 3 * C, B, 8, D, T, T, 0, None, ptr(out), C, stream())
+        else:
+            q = torch.randn(B, T, C, device="cuda").half()
+            kv = torch.randn(2, Tk, 2 * C, device="cuda").half()
+            kvi = (torch.arange(B, device="cuda", dtype=torch.int32) % 2).contiguous()
+            out = torch.empty(B, T, C, device="cuda", dtype=torch.float16)
+            args = (ptr(q), ptr(kv[..., :C]), ptr(kv[..., C:]), C, 2 * C, 2 * C, T * C, Tk * 2 * C, Tk * 2 * C, B, 8, D, T, Tk, 2,
+                    ptr(kvi), ptr(out), C, stream())
+        for _ in range(3):
+            check(lib.dm_op_attention(*args))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            check(lib.dm_op_attention(*args))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        fl = 4.0 * B * 8 * T * Tk * D
+        print(f"BENCH attn B{B} T{T} Tk{Tk} D{D} DM_ATTN2={os.environ.get('DM_ATTN2','1')}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s", flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -243,5 +276,7 @@ if __name__ == "__main__":
         ok &= attn_cases()
     if which in ("bench", "all"):
         bench_conv()
+    if which in ("benchattn",):
+        bench_attn()
     print("ALL OK" if ok else "SOME FAILED", f"({time.time()-t0:.1f}s)")
     sys.exit(0 if ok else 1)

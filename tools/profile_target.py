@@ -74,5 +74,44 @@ def ops():
     torch.cuda.cudart().cudaProfilerStop()
 
 
+def attn():
+    """self-attention d=40 T=4096 alone (B from DM_BF, default 8), for ncu --set full"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gpu_optest as o
+
+    lib, ptr, stream = o.lib, o.ptr, o.stream
+    B, T, D = int(os.environ.get("DM_BF", "8")), 4096, 40
+    C = 8 * D
+    qkv = torch.randn(B, T, 3 * C, device="cuda").half()
+    out = torch.empty(B, T, C, device="cuda", dtype=torch.float16)
+    args = (ptr(qkv[..., :C]), ptr(qkv[..., C:2 * C]), ptr(qkv[..., 2 * C:]), 3 * C, 3 * C, 3 * C, T * 3 * C, T * 3 * C, T * 3 * C, B, 8, D, T, T, 0, None, ptr(out), C, stream())
+    for _ in range(2):
+        o.check(lib.dm_op_attention(*args))
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
+    o.check(lib.dm_op_attention(*args))
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+
+
+def layers():
+    """per-layer CUDA-event table of one micro-batch (DMPROF lines on stdout)"""
+    from diff_mining_b200.engine import Engine
+    from oracle import sd15
+
+    os.environ["DM_PROFILE_VERBOSE"] = "1"
+    usd = sd15.make_synthetic_weights(sd15.unet_param_shapes(), seed=0)
+    eng = Engine(0)
+    eng.load_state_dict(usd, "unet.")
+    eng.finalize()
+    g = torch.Generator().manual_seed(5)
+    for i in range(2):
+        eng.set_context(i, torch.randn(77, 768, generator=g))
+    Bf = int(os.environ.get("DM_BF", "32"))
+    lat = int(os.environ.get("DM_LAT", "64"))
+    pr = eng.profile_unet(Bf, lat, lat, iters=5)
+    print("DMPROF_TOTAL", pr)
+
+
 if __name__ == "__main__":
-    {"unet": unet, "ops": ops}[sys.argv[1]]()
+    {"unet": unet, "ops": ops, "layers": layers, "attn": attn}[sys.argv[1]]()
