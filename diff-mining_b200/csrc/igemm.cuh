@@ -11,8 +11,16 @@
 // K-major layout tcgen05.mma consumes.  Weights Wt[N, K] (K ordered like the segment list) arrive by 2-D TMA.
 //
 // Persistent CTAs, warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc),
-// warps 2..5 = epilogue (TMEM -> regs -> bias/temb/SiLU/GEGLU/residual -> global).  Two TMEM accumulator
-// buffers let the epilogue of tile i overlap the main loop of tile i+1.
+// warps 2..9 = two epilogue warpgroups.  Two TMEM accumulator buffers let the epilogue of tile i overlap the
+// main loop of tile i+1.
+//
+// Epilogue (staged): the accumulator tile is drained in chunks of 32 output columns, alternating between the two
+// warpgroups.  A chunk lives in a 128 x 32 fp16 shared-memory buffer (64-byte swizzle) of the warpgroup's ring:
+// the residual tile is PREFETCHED into it by TMA (several chunks ahead, so its HBM latency is never exposed), each
+// thread (= one accumulator row) combines TMEM + bias + row-bias + activation + residual in packed fp16 arithmetic
+// (HADD2 / HMUL2 round exactly like the reference's fp16 tensor adds), writes the result back in place, and one
+// elected thread hands the buffer to a TMA store, which clips the M / N tails.  No per-thread strided global
+// access remains.  The "direct" variant (fp32 output, N-tiles narrower than 32) keeps plain global stores.
 #pragma once
 #include "ptx.cuh"
 
@@ -21,6 +29,9 @@ namespace dm {
 constexpr int IG_MAX_SEG = 24;
 constexpr int IG_BM = 128;
 constexpr int IG_BK = 64;
+constexpr int IG_CW = 32;                           // output columns per epilogue chunk
+constexpr int IG_CHUNK_BYTES = IG_BM * IG_CW * 2;   // 8 KB
+constexpr int IG_THREADS = 64 + 256;
 
 struct IgSeg {
   int16_t src, dy, dx, pad_;
@@ -30,6 +41,8 @@ struct IgSeg {
 struct alignas(64) IgMaps {
   CUtensorMap a[2];
   CUtensorMap b;
+  CUtensorMap c;  // output   [Nimg, H, W, ld_out], box [nt][ht][wt][32], 64B swizzle (staged epilogue only)
+  CUtensorMap r;  // residual [Nimg, H, W, ld_res], same box
 };
 
 struct IgParams {
@@ -50,32 +63,63 @@ struct IgParams {
   int out_f32, geglu, act_silu;
 };
 
-template <int BN>
+template <int BN, bool DIRECT>
 struct IgCfg {
   static constexpr int A_BYTES = IG_BM * IG_BK * 2;
   static constexpr int B_BYTES = BN * IG_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int RAW_STAGES = (220 * 1024) / STAGE_BYTES;
+  static constexpr int NBG = DIRECT ? 0 : (BN >= 256 ? 2 : 4);  // chunk buffers per epilogue warpgroup
+  static constexpr int LOOKAHEAD = NBG >= 4 ? 2 : 1;             // residual prefetch distance (chunks)
+  static constexpr int RING_BYTES = 2 * NBG * IG_CHUNK_BYTES;
+  static constexpr int BIAS_BYTES = 2 * BN * 4;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int RAW_STAGES = (232448 - RING_BYTES - BIAS_BYTES - BAR_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int THREADS = 192;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RING_BYTES + BIAS_BYTES + BAR_BYTES;
+  static_assert(STAGES >= 3, "pipeline too shallow");
+  static_assert(2 * STAGES + 4 + 4 * 2 + 1 <= BAR_BYTES / 8, "barrier area");
 };
 
-template <int BN>
-__global__ void __launch_bounds__(192, 1) igemm_kernel(const __grid_constant__ IgMaps maps, const IgParams p) {
-  using Cfg = IgCfg<BN>;
+// Phi(x) * x with erfc from Abramowitz-Stegun 7.1.26 (|abs err| < 4.3e-7 on the result: within one fp16 ulp of
+// the erf formulation everywhere, closer to the exact value than 0.5*x*(1+erff(x/sqrt2)) on the negative tail).
+// Two MUFU ops and ~12 FMA-pipe ops, branch-free.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.f));
+  float pl = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  pl = fmaf(t, pl, 0.5f * 1.421413741f);
+  pl = fmaf(t, pl, 0.5f * -0.284496736f);
+  pl = fmaf(t, pl, 0.5f * 0.254829592f);
+  const float q = pl * t * fast_exp2(-1.4426950408889634f * z * z);  // 0.5 * erfc(|x| / sqrt 2)
+  return x * (x < 0.f ? q : 1.f - q);
+}
+
+__device__ __forceinline__ __half2 u2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int BN, bool DIRECT>
+__global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_constant__ IgMaps maps, const IgParams p) {
+  using Cfg = IgCfg<BN, DIRECT>;
   constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NBG = Cfg::NBG;
+  extern __shared__ __align__(1024) uint8_t smem[];  // 128B-swizzled tiles need 1024-byte alignment
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* smA = smem;
   uint8_t* smB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* smC = smem + STAGES * Cfg::STAGE_BYTES;
+  float* smBias = reinterpret_cast<float*>(smC + Cfg::RING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smC + Cfg::RING_BYTES + Cfg::BIAS_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* rfull = bars + 2 * STAGES + 4;  // [2 groups][NBG]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,11 +131,13 @@ __global__ void __launch_bounds__(192, 1) igemm_kernel(const __grid_constant__ I
     }
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 4);
-    mbar_init(&tempty[1], 4);
+    mbar_init(&tempty[0], 8);
+    mbar_init(&tempty[1], 8);
+    for (int i = 0; i < 8; ++i) mbar_init(&rfull[i], 1);
     fence_barrier_init();
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.b);
+    if constexpr (!DIRECT) tma_prefetch_desc(&maps.c);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -163,122 +209,285 @@ __global__ void __launch_bounds__(192, 1) igemm_kernel(const __grid_constant__ I
       }
     }
   } else {
-    // ============================== epilogue (4 warps) ==============================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // ============================== epilogue (2 warpgroups) ==============================
+    const int ew = warp - 2;        // 0..7
+    const int eg = ew >> 2;         // warpgroup
+    const int quarter = warp & 3;   // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;
-    constexpr int CH = (BN % 32 == 0) ? 32 : 16;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int acc = lt & 1;
-      const uint32_t acc_phase = (lt >> 1) & 1;
-      const int mt = tile / p.n_tiles, ntile = tile % p.n_tiles;
-      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
-      const int x = (tx << p.wt_log) + (r & ((1 << p.wt_log) - 1));
-      const int y = (ty << p.ht_log) + ((r >> p.wt_log) & ((1 << p.ht_log) - 1));
-      const int n = (tn << p.nt_log) + (r >> (p.wt_log + p.ht_log));
-      const bool row_ok = (x < p.W) && (y < p.H) && (n < p.Nimg);
-      const long long m = (static_cast<long long>(n) * p.H + y) * p.W + x;
+    if constexpr (DIRECT) {
+      constexpr int CH = (BN % 32 == 0) ? 32 : 16;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        const uint32_t acc_phase = (lt >> 1) & 1;
+        const int mt = tile / p.n_tiles, ntile = tile % p.n_tiles;
+        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
+        const int x = (tx << p.wt_log) + (r & ((1 << p.wt_log) - 1));
+        const int y = (ty << p.ht_log) + ((r >> p.wt_log) & ((1 << p.ht_log) - 1));
+        const int n = (tn << p.nt_log) + (r >> (p.wt_log + p.ht_log));
+        const bool row_ok = (x < p.W) && (y < p.H) && (n < p.Nimg);
+        const long long m = (static_cast<long long>(n) * p.H + y) * p.W + x;
 
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += CH) {
-        uint32_t raw[CH];
-        if constexpr (CH == 32) tmem_ld_x32(taddr + c0, raw);
-        else tmem_ld_x16(taddr + c0, raw);
-        tmem_wait_ld();
-        const int col0 = ntile * BN + c0;
-        int nvalid = p.N - col0;
-        nvalid = nvalid > CH ? CH : nvalid;
-        if (!row_ok || nvalid <= 0) continue;
-        float v[CH];
+        for (int c0 = eg * CH; c0 < BN; c0 += 2 * CH) {
+          uint32_t raw[CH];
+          if constexpr (CH == 32) tmem_ld_x32(taddr + c0, raw);
+          else tmem_ld_x16(taddr + c0, raw);
+          tmem_wait_ld();
+          const int col0 = ntile * BN + c0;
+          int nvalid = p.N - col0;
+          nvalid = nvalid > CH ? CH : nvalid;
+          if (!row_ok || nvalid <= 0) continue;
+          float v[CH];
 #pragma unroll
-        for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(raw[i]);
+          for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(raw[i]);
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < CH; i += 4) {
+              if (i < nvalid) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+              }
+            }
+          }
+          if (p.out_f32) {
+            float* o = reinterpret_cast<float*>(p.out) + m * p.ld_out + col0;
+#pragma unroll
+            for (int i = 0; i < CH; i += 4)
+              if (i < nvalid) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            continue;
+          }
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] = round_h(v[i]);
+          if (p.rowbias) {
+            const __half* rb = p.rowbias + static_cast<long long>(n) * p.ld_rowbias + col0;
+#pragma unroll
+            for (int i = 0; i < CH; i += 8) {
+              if (i < nvalid) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(rb + i));
+                const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __half22float2(h[j]);
+                  v[i + 2 * j] = round_h(v[i + 2 * j] + f.x);
+                  v[i + 2 * j + 1] = round_h(v[i + 2 * j + 1] + f.y);
+                }
+              }
+            }
+          }
+          if (p.act_silu) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = round_h(silu_f(v[i]));
+          }
+          if (p.residual) {
+            const __half* rs = p.residual + m * p.ld_res + col0;
+#pragma unroll
+            for (int i = 0; i < CH; i += 8) {
+              if (i < nvalid) {
+                const uint4 q = *reinterpret_cast<const uint4*>(rs + i);
+                const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __half22float2(h[j]);
+                  v[i + 2 * j] += f.x;
+                  v[i + 2 * j + 1] += f.y;
+                }
+              }
+            }
+          }
+          __half* o = reinterpret_cast<__half*>(p.out) + m * p.ld_out + col0;
+#pragma unroll
+          for (int i = 0; i < CH; i += 8) {
+            if (i < nvalid) {
+              *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_h2(v[i], v[i + 1]), pack_h2(v[i + 2], v[i + 3]),
+                                                            pack_h2(v[i + 4], v[i + 5]), pack_h2(v[i + 6], v[i + 7]));
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
+    } else {
+      // ---------------- staged epilogue ----------------
+      const bool leader = (ew & 3) == 0 && lane == 0;
+      const int gtid = (ew & 3) * 32 + lane;
+      const int bar_id = 1 + eg;
+      uint8_t* ring = smC + eg * NBG * IG_CHUNK_BYTES;
+      float* sbias = smBias + eg * BN;
+      uint64_t* rf = rfull + eg * NBG;
+      const bool has_res = p.residual != nullptr;
+      const int acc_per_chunk = p.geglu ? 2 * IG_CW : IG_CW;
+      const int nchunk = BN / acc_per_chunk;
+      const int out_tile_cols = p.geglu ? BN / 2 : BN;
+      // byte offset of 16-byte piece j of this thread's row inside a chunk buffer (64B swizzle: Swizzle<2,4,3>)
+      const uint32_t row_off = static_cast<uint32_t>(r) * 64u;
+      const uint32_t sw = (static_cast<uint32_t>(r) >> 1) & 3u;
+
+      // iterator over this warpgroup's chunks: chunk c of local tile lt belongs to group (lt*nchunk + c) & 1
+      struct It {
+        int tile, lt, c;
+      };
+      auto first_c = [&](int lt_) { return (eg ^ (lt_ * nchunk)) & 1; };
+      auto settle = [&](It& it) {  // skip tiles in which this group owns no chunk
+        while (it.tile < num_tiles && it.c >= nchunk) {
+          it.tile += gridDim.x;
+          it.lt += 1;
+          it.c = first_c(it.lt);
+        }
+      };
+      auto advance = [&](It& it) {
+        it.c += 2;
+        settle(it);
+      };
+      auto coords = [&](const It& it, int& col, int& x0, int& y0, int& n0) {
+        const int mt = it.tile / p.n_tiles, ntile = it.tile % p.n_tiles;
+        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
+        x0 = tx << p.wt_log; y0 = ty << p.ht_log; n0 = tn << p.nt_log;
+        col = ntile * out_tile_cols + it.c * IG_CW;
+      };
+      It pf{static_cast<int>(blockIdx.x), 0, first_c(0)};  // residual prefetch cursor (leader only)
+      settle(pf);
+      int pf_k = 0;
+      auto prefetch_one = [&]() {
+        if (pf.tile < num_tiles) {
+          int col, x0, y0, n0;
+          coords(pf, col, x0, y0, n0);
+          const int b = pf_k % NBG;
+          mbar_arrive_expect_tx(&rf[b], IG_CHUNK_BYTES);
+          tma_load_4d(ring + b * IG_CHUNK_BYTES, &maps.r, &rf[b], col, x0, y0, n0);
+        }
+        ++pf_k;
+        advance(pf);
+      };
+      if (leader && has_res) {
+        tma_prefetch_desc(&maps.r);
+        for (int i = 0; i < Cfg::LOOKAHEAD; ++i) prefetch_one();
+      }
+
+      int k = 0;  // chunks processed by this warpgroup
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        const uint32_t acc_phase = (lt >> 1) & 1;
+        const int ntile = tile % p.n_tiles;
         if (p.bias) {
-#pragma unroll
-          for (int i = 0; i < CH; i += 4) {
-            if (i < nvalid) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-              v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-            }
+          for (int i = gtid; i < BN; i += 128) {
+            const int col = ntile * BN + i;
+            sbias[i] = col < p.N ? __ldg(p.bias + col) : 0.f;
           }
+          named_bar_sync(bar_id, 128);
         }
-        if (p.out_f32) {
-          float* o = reinterpret_cast<float*>(p.out) + m * p.ld_out + col0;
-#pragma unroll
-          for (int i = 0; i < CH; i += 4)
-            if (i < nvalid) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          continue;
-        }
-#pragma unroll
-        for (int i = 0; i < CH; ++i) v[i] = round_h(v[i]);
+        const __half* rb = nullptr;
         if (p.rowbias) {
-          const __half* rb = p.rowbias + static_cast<long long>(n) * p.ld_rowbias + col0;
+          const int mt = tile / p.n_tiles;
+          const int tn = mt / (p.tiles_x * p.tiles_y);
+          int n = (tn << p.nt_log) + (r >> (p.wt_log + p.ht_log));
+          n = n < p.Nimg ? n : p.Nimg - 1;
+          rb = p.rowbias + static_cast<long long>(n) * p.ld_rowbias + ntile * BN;
+        }
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+        const int c_first = first_c(lt);
+#pragma unroll 1
+        for (int c = c_first; c < nchunk; c += 2, ++k) {
+          const int b = k % NBG;
+          uint8_t* buf = ring + b * IG_CHUNK_BYTES + row_off;
+          uint32_t pk[16];  // 32 output halves
+          if (p.geglu) {
+            uint32_t raw[64];
+            tmem_ld_x32(taddr + c * 64, raw);
+            tmem_ld_x32(taddr + c * 64 + 32, raw + 32);
+            tmem_wait_ld();
+            const float4* sb4 = reinterpret_cast<const float4*>(sbias + c * 64);
 #pragma unroll
-          for (int i = 0; i < CH; i += 8) {
-            if (i < nvalid) {
-              const uint4 q = __ldg(reinterpret_cast<const uint4*>(rb + i));
-              const __half2* h = reinterpret_cast<const __half2*>(&q);
+            for (int i = 0; i < 16; ++i) {
+              // accumulator columns 4i..4i+3 = (value, gate, value, gate) -> output columns 2i, 2i+1
+              float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) bb = sb4[i];
+              const __half2 val = __floats2half2_rn(__uint_as_float(raw[4 * i]) + bb.x, __uint_as_float(raw[4 * i + 2]) + bb.z);
+              const __half2 gate = __floats2half2_rn(__uint_as_float(raw[4 * i + 1]) + bb.y, __uint_as_float(raw[4 * i + 3]) + bb.w);
+              const float2 gf = __half22float2(gate);
+              const __half2 act = __floats2half2_rn(gelu_fast(gf.x), gelu_fast(gf.y));
+              pk[i] = h2u(__hmul2(val, act));
+            }
+          } else {
+            uint32_t raw[32];
+            tmem_ld_x32(taddr + c * 32, raw);
+            tmem_wait_ld();
+            const float4* sb4 = reinterpret_cast<const float4*>(sbias + c * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) bb = sb4[i];
+              pk[2 * i] = h2u(__floats2half2_rn(__uint_as_float(raw[4 * i]) + bb.x, __uint_as_float(raw[4 * i + 1]) + bb.y));
+              pk[2 * i + 1] = h2u(__floats2half2_rn(__uint_as_float(raw[4 * i + 2]) + bb.z, __uint_as_float(raw[4 * i + 3]) + bb.w));
+            }
+            if (rb) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h[j]);
-                v[i + 2 * j] = round_h(v[i + 2 * j] + f.x);
-                v[i + 2 * j + 1] = round_h(v[i + 2 * j + 1] + f.y);
+                if (ntile * BN + c * 32 + j * 8 >= p.N) break;
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(rb + c * 32 + j * 8));
+                pk[4 * j] = h2u(__hadd2(u2h(pk[4 * j]), u2h(q.x)));
+                pk[4 * j + 1] = h2u(__hadd2(u2h(pk[4 * j + 1]), u2h(q.y)));
+                pk[4 * j + 2] = h2u(__hadd2(u2h(pk[4 * j + 2]), u2h(q.z)));
+                pk[4 * j + 3] = h2u(__hadd2(u2h(pk[4 * j + 3]), u2h(q.w)));
+              }
+            }
+            if (p.act_silu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float2 f = __half22float2(u2h(pk[i]));
+                pk[i] = h2u(__floats2half2_rn(silu_f(f.x), silu_f(f.y)));
               }
             }
           }
-        }
-        if (p.act_silu) {
+          if (c + 2 >= nchunk) {  // last TMEM read of this tile by this warp: hand the accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          if (has_res) {
+            mbar_wait(&rf[b], (k / NBG) & 1);
 #pragma unroll
-          for (int i = 0; i < CH; ++i) v[i] = round_h(silu_f(v[i]));
-        }
-        if (p.geglu) {
-          // weight rows interleaved: even column = value, odd column = gate -> out[m, col/2]
-          __half* o = reinterpret_cast<__half*>(p.out) + m * p.ld_out + (col0 >> 1);
-#pragma unroll
-          for (int i = 0; i < CH; i += 16) {
-            if (i < nvalid) {
-              uint32_t pk[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float a0 = round_h(v[i + 4 * j] * round_h(gelu_erf_f(v[i + 4 * j + 1])));
-                const float a1 = round_h(v[i + 4 * j + 2] * round_h(gelu_erf_f(v[i + 4 * j + 3])));
-                pk[j] = pack_h2(a0, a1);
-              }
-              *reinterpret_cast<uint4*>(o + (i >> 1)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            for (int j = 0; j < 4; ++j) {
+              const uint4 q = *reinterpret_cast<const uint4*>(buf + ((static_cast<uint32_t>(j) ^ sw) << 4));
+              pk[4 * j] = h2u(__hadd2(u2h(pk[4 * j]), u2h(q.x)));
+              pk[4 * j + 1] = h2u(__hadd2(u2h(pk[4 * j + 1]), u2h(q.y)));
+              pk[4 * j + 2] = h2u(__hadd2(u2h(pk[4 * j + 2]), u2h(q.z)));
+              pk[4 * j + 3] = h2u(__hadd2(u2h(pk[4 * j + 3]), u2h(q.w)));
             }
           }
-          continue;
-        }
-        if (p.residual) {
-          const __half* rs = p.residual + m * p.ld_res + col0;
 #pragma unroll
-          for (int i = 0; i < CH; i += 8) {
-            if (i < nvalid) {
-              const uint4 q = *reinterpret_cast<const uint4*>(rs + i);
-              const __half2* h = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h[j]);
-                v[i + 2 * j] += f.x;
-                v[i + 2 * j + 1] += f.y;
-              }
-            }
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(buf + ((static_cast<uint32_t>(j) ^ sw) << 4)) =
+                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          fence_proxy_async_smem();
+          if (leader) {
+            // buffer (k + LOOKAHEAD) % NBG must have been drained by the store of chunk k + LOOKAHEAD - NBG
+            tma_store_wait_read<NBG - Cfg::LOOKAHEAD - 1>();
+          }
+          named_bar_sync(bar_id, 128);
+          if (leader) {
+            const int mt = tile / p.n_tiles;
+            const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
+            tma_store_4d(&maps.c, ring + b * IG_CHUNK_BYTES, ntile * out_tile_cols + c * IG_CW, tx << p.wt_log,
+                         ty << p.ht_log, tn << p.nt_log);
+            tma_store_commit();
+            if (has_res) prefetch_one();
           }
         }
-        __half* o = reinterpret_cast<__half*>(p.out) + m * p.ld_out + col0;
-#pragma unroll
-        for (int i = 0; i < CH; i += 8) {
-          if (i < nvalid) {
-            *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_h2(v[i], v[i + 1]), pack_h2(v[i + 2], v[i + 3]),
-                                                          pack_h2(v[i + 4], v[i + 5]), pack_h2(v[i + 6], v[i + 7]));
-          }
+        if (c_first >= nchunk) {  // this group owns no chunk of the tile: still release the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (leader) tma_store_wait_all();
     }
   }
 

@@ -32,7 +32,7 @@ static EncodeTiledFn encode_fn() {
 
 // fp16 tensor, dims innermost-first, strides (bytes) for dims 1..rank-1, 128B swizzle, zero OOB fill
 static void make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_b,
-                      const uint32_t* box) {
+                      const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) {
@@ -47,7 +47,7 @@ static void make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t*
   }
   DM_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "tensor map: base not 16-byte aligned");
   CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
 }
@@ -142,6 +142,26 @@ IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms) {
   p.out = d.out; p.ld_out = d.ld_out;
   p.out_f32 = d.out_f32; p.geglu = d.geglu; p.act_silu = d.act_silu;
   DM_CHECK(d.out != nullptr && d.ld_out % 8 == 0, "igemm: bad output");
+  // staged epilogue (TMA store / residual prefetch) unless the output is fp32 or the N-tile is narrower than a chunk
+  op.direct = (d.out_f32 || op.bn < 32) ? 1 : 0;
+  DM_CHECK(!d.geglu || (op.bn % 64 == 0 && !op.direct), "igemm: GEGLU needs an N-tile that is a multiple of 64");
+  DM_CHECK(!d.geglu || (!d.residual && !d.rowbias && !d.act_silu), "igemm: GEGLU excludes the other epilogue options");
+  if (!op.direct) {
+    const int Cout = d.geglu ? d.N / 2 : d.N;
+    auto cmap = [&](CUtensorMap* m, const void* ptr, long long ld) {
+      DM_CHECK(ld % 8 == 0 && ld >= Cout, "igemm: output / residual row stride must be a multiple of 8 elements");
+      const uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H),
+                                static_cast<uint64_t>(d.Nimg)};
+      const uint64_t st[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * d.W,
+                              static_cast<uint64_t>(ld) * 2 * d.W * d.H};
+      const uint32_t box[4] = {IG_CW, static_cast<uint32_t>(1 << p.wt_log), static_cast<uint32_t>(1 << p.ht_log),
+                               static_cast<uint32_t>(1 << p.nt_log)};
+      make_tmap(m, ptr, 4, dims, st, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    };
+    cmap(&op.maps.c, d.out, d.ld_out);
+    if (d.residual) cmap(&op.maps.r, d.residual, d.ld_res);
+    else op.maps.r = op.maps.c;
+  }
   for (int s = 0; s < d.nsrc; ++s) {
     const ActView& a = d.src[s];
     DM_CHECK(a.ptr && a.C > 0 && a.pix_stride >= a.C, "igemm: bad source view");
@@ -165,25 +185,37 @@ IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms) {
   return op;
 }
 
-template <int BN>
+template <int BN, bool DIRECT>
 static void igemm_launch_bn(const IgemmOp& op, cudaStream_t s) {
   static bool configured = false;
+  using Cfg = IgCfg<BN, DIRECT>;
   if (!configured) {
-    DM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, IgCfg<BN>::SMEM_BYTES));
+    DM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  igemm_kernel<BN><<<op.grid, 192, IgCfg<BN>::SMEM_BYTES, s>>>(op.maps, op.p);
+  igemm_kernel<BN, DIRECT><<<op.grid, IG_THREADS, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
   DM_CUDA(cudaGetLastError());
 }
 
 void igemm_launch(const IgemmOp& op, cudaStream_t s) {
+  if (op.direct) {
+    switch (op.bn) {
+      case 256: igemm_launch_bn<256, true>(op, s); break;
+      case 160: igemm_launch_bn<160, true>(op, s); break;
+      case 128: igemm_launch_bn<128, true>(op, s); break;
+      case 64: igemm_launch_bn<64, true>(op, s); break;
+      case 32: igemm_launch_bn<32, true>(op, s); break;
+      case 16: igemm_launch_bn<16, true>(op, s); break;
+      default: DM_CHECK(false, "igemm: unsupported BN " + std::to_string(op.bn) + " for the direct epilogue");
+    }
+    return;
+  }
   switch (op.bn) {
-    case 256: igemm_launch_bn<256>(op, s); break;
-    case 160: igemm_launch_bn<160>(op, s); break;
-    case 128: igemm_launch_bn<128>(op, s); break;
-    case 64: igemm_launch_bn<64>(op, s); break;
-    case 32: igemm_launch_bn<32>(op, s); break;
-    case 16: igemm_launch_bn<16>(op, s); break;
+    case 256: igemm_launch_bn<256, false>(op, s); break;
+    case 160: igemm_launch_bn<160, false>(op, s); break;
+    case 128: igemm_launch_bn<128, false>(op, s); break;
+    case 64: igemm_launch_bn<64, false>(op, s); break;
+    case 32: igemm_launch_bn<32, false>(op, s); break;
     default: DM_CHECK(false, "igemm: unsupported BN " + std::to_string(op.bn));
   }
 }

@@ -60,6 +60,7 @@ struct IgemmOp {
   IgMaps maps;
   IgParams p;
   int bn = 0, grid = 0;
+  int direct = 0;  // 1 = plain global-store epilogue (fp32 output or N-tile < 32 columns)
   double flops = 0;
 };
 
