@@ -4,14 +4,17 @@
 // which is MUFU.EX2-bound at these head dims (128x128 exps per tile = 1024 SM cycles vs <= 640 tensor cycles) --
 // never waits for the tensor pipe:
 //
-//   one CTA = one (batch, head, 256-query block) = two 128-row Q tiles, one per softmax warpgroup
-//   warp 0      TMA producer: Q once, then K / V tiles through ST-deep rings
-//   warps 1, 2  MMA issuers, one per Q tile: S_q = Q_q K_j^T  and  O_q += P_q V_j   (tcgen05, fp32 in TMEM)
-//   warp 3      idle
-//   warps 4-7   softmax warpgroup 0 (thread = query row of tile 0)
-//   warps 8-11  softmax warpgroup 1 (tile 1)
+//   one CTA = one (batch, head, 256-query block) = two 128-row Q tiles, one per softmax group
+//   warp 0       TMA producer: Q once, then K / V tiles through ST-deep rings
+//   warps 1, 2   MMA issuers, one per Q tile: S_q = Q_q K_j^T  and  O_q += P_q V_j   (tcgen05, fp32 in TMEM)
+//   warp 3       idle
+//   warps 4-11   softmax group 0 (tile 0): TWO threads per query row, each owning half of the key columns
+//   warps 12-19  softmax group 1 (tile 1)
+// Sixteen softmax warps = four per SM sub-partition: while one warp sits in a MUFU burst, waits for S or pulls TMEM,
+// three others can issue, which is what keeps the XU pipe (the bound at these head dims) busy.  The two threads
+// of a row exchange their half-row maxima / sums through shared memory (one named barrier per KV tile).
 //
-// A softmax thread pulls its whole S row into registers in one TMEM pass and releases S at once (s_free), so
+// A softmax thread pulls its half S row into registers in one TMEM pass and releases S at once (s_free), so
 // QK^T of tile j+1 is issued while the exponentials of tile j are still being computed; P is double-buffered in
 // shared memory so P_q V_j runs under the softmax of tile j+1 without a wait; the two warpgroups are started half
 // a tile apart so that one of them always feeds the MUFU pipe.  Row max via 3-input FMNMX, scale/offset and row sums via packed f32x2 FMA/ADD.
@@ -30,10 +33,14 @@ struct Attn2Cfg {
   static constexpr int KV_BYTES = NCH * BKV * 128;
   static constexpr int P_TILE_BYTES = 128 * BKV * 2;  // one P buffer; two per Q tile
   static constexpr int NBAR = 1 + 4 * ST + 10;
-  static constexpr int SMEM_BYTES = 2 * Q_TILE_BYTES + 2 * ST * KV_BYTES + 4 * P_TILE_BYTES + 1024 + NBAR * 8 + 64;
+  static constexpr int SMEM_BYTES = 2 * Q_TILE_BYTES + 2 * ST * KV_BYTES + 4 * P_TILE_BYTES + NBAR * 8 + 64;
+  // Half-row exchange slots live in the never-read tail of the Q tile: logical 16-byte chunk 6 of every 128-byte
+  // row of the last 64-channel chunk holds channels >= 48 (+64*(NCH-1)), which no MMA touches.
+  static_assert(D - 64 * (NCH - 1) <= 48, "no free chunk in the Q tile for the exchange slots");
+  static constexpr int HC = BKV / 2;  // key columns per softmax thread
   static constexpr int O_COL = 2 * BKV;  // S_q at columns [q*BKV, (q+1)*BKV), O_q at O_COL + q*DK
   static constexpr int TMEM_COLS = 512;
-  static constexpr int THREADS = 384;
+  static constexpr int THREADS = 128 + 512;
   static_assert(2 * BKV + 2 * DK <= 512, "TMEM budget");
   static_assert(BKV == 64 || BKV == 128, "BKV");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -63,12 +70,16 @@ __device__ __forceinline__ uint64_t add_f2(uint64_t a, uint64_t b) {
   return d;
 }
 
+__device__ __forceinline__ void named_bar_sync256(int id) {
+  asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory");
+}
+
 template <int D, int BKV, int ST>
-__global__ void __launch_bounds__(384, 1) attention2_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
+__global__ void __launch_bounds__(640, 1) attention2_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
   using Cfg = Attn2Cfg<D, BKV, ST>;
   constexpr int DK = Cfg::DK, NCH = Cfg::NCH;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];  // 128B-swizzled tiles need 1024-byte alignment
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + 2 * Cfg::Q_TILE_BYTES;
   uint8_t* sV = sK + ST * Cfg::KV_BYTES;
@@ -100,8 +111,8 @@ __global__ void __launch_bounds__(384, 1) attention2_kernel(const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 4);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&s_free[i], 8);
+      mbar_init(&p_full[i], 8);
       mbar_init(&o_full[2 * i], 1);
       mbar_init(&o_full[2 * i + 1], 1);
     }
@@ -192,67 +203,80 @@ __global__ void __launch_bounds__(384, 1) attention2_kernel(const __grid_constan
       }
     }
   } else if (warp >= 4) {
-    // ============================== softmax warpgroups ==============================
-    const int wg = (warp - 4) >> 2;
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // ============================== softmax groups ==============================
+    constexpr int HC = Cfg::HC;
+    const int wg = (warp - 4) >> 3;
+    const int half = ((warp - 4) >> 2) & 1;  // which half of the key columns of the tile
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
+    const int bar_id = 2 + wg;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t t_s = t_lane + wg * BKV;
+    const uint32_t t_s = t_lane + wg * BKV + half * HC;
     const uint32_t t_o = t_lane + Cfg::O_COL + wg * DK;
     uint8_t* sPq = sP + 2 * wg * Cfg::P_TILE_BYTES + row * 128;
     uint64_t* o_full_q = o_full + 2 * wg;
+    // exchange slots [parity][half] of this row (see Attn2Cfg)
+    float* xrow = reinterpret_cast<float*>(sQ + wg * Cfg::Q_TILE_BYTES + (NCH - 1) * 16384 + row * 128 +
+                                           ((6 ^ (row & 7)) << 4));
+    float* xmine = xrow + half;
+    float* xpeer = xrow + (half ^ 1);
     const float sc = p.scale_log2;
     const float thr = 8.f / sc;  // lazy rescale threshold in raw-score units (2^8 headroom)
     const uint64_t sc2 = pack_f2(sc, sc);
     float m_ref = -INFINITY;
     uint64_t l2 = pack_f2(0.f, 0.f);
+    // O columns (in 16-column TMEM chunks) this thread rescales on the rare path
+    constexpr int NCH16 = DK / 16;
+    const int ch_lo = half == 0 ? 0 : (NCH16 + 1) / 2, ch_hi = half == 0 ? (NCH16 + 1) / 2 : NCH16;
 
     for (int j = 0; j < nkv; ++j) {
       const uint32_t jp = j & 1;
       mbar_wait(&s_full[wg], jp);
       tc_fence_after();
-      uint32_t raw[BKV];
+      uint32_t raw[HC];
 #pragma unroll
-      for (int c0 = 0; c0 < BKV; c0 += 32) tmem_ld_x32(t_s + c0, raw + c0);
+      for (int c0 = 0; c0 < HC; c0 += 32) tmem_ld_x32(t_s + c0, raw + c0);
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[wg]);
 
-      const int kbase = j * BKV;
-      if (kbase + BKV > p.Tk) {  // ragged last tile (cross-attention: 77 keys)
+      const int kbase = j * BKV + half * HC;
+      if (kbase + HC > p.Tk) {  // ragged last tile (cross-attention: 77 keys)
 #pragma unroll
-        for (int i = 0; i < BKV; ++i)
+        for (int i = 0; i < HC; ++i)
           if (kbase + i >= p.Tk) raw[i] = 0xff800000u;  // -inf
       }
       float mx0 = __uint_as_float(raw[0]), mx1 = __uint_as_float(raw[1]);
 #pragma unroll
-      for (int i = 2; i < BKV; i += 4) {
+      for (int i = 2; i < HC; i += 4) {
         mx0 = fmax3(mx0, __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
-        if (i + 2 < BKV) mx1 = fmax3(mx1, __uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]));
+        if (i + 2 < HC) mx1 = fmax3(mx1, __uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]));
       }
-      const float mx = fmaxf(mx0, mx1);
-      const bool grow = mx > m_ref + thr;  // true on the first tile (m_ref = -inf)
+      // the row's other half lives in the partner thread (warp + 4): exchange the half-row maxima
+      xmine[jp * 2] = fmaxf(mx0, mx1);
+      named_bar_sync256(bar_id);
+      const float mx = fmaxf(fmaxf(mx0, mx1), xpeer[jp * 2]);
+      const bool grow = mx > m_ref + thr;  // true on the first tile (m_ref = -inf); identical in both halves
       const float m_new = grow ? mx : m_ref;
       const float alpha = grow ? exp2f((m_ref - m_new) * sc) : 1.f;
       if (j > 0 && __any_sync(0xffffffffu, grow)) {
         // rare: O_q must be rescaled, so PV(j-1) has to be complete first
         mbar_wait(&o_full_q[jp ^ 1], ((j - 1) >> 1) & 1);
         tc_fence_after();
-#pragma unroll
-        for (int c0 = 0; c0 < DK; c0 += 16) {
+        for (int ch = ch_lo; ch < ch_hi; ++ch) {
           uint32_t o[16];
-          tmem_ld_x16(t_o + c0, o);
+          tmem_ld_x16(t_o + ch * 16, o);
           tmem_wait_ld();
 #pragma unroll
           for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_x16(t_o + c0, o);
+          tmem_st_x16(t_o + ch * 16, o);
         }
         tmem_wait_st();
       }
       // P buffer j&1 was last read by PV(j-2)
       if (j >= 2) mbar_wait(&o_full_q[jp], ((j - 2) >> 1) & 1);
-      if (j == 0 && wg == 1) asm volatile("bar.sync 1, 256;" ::: "memory");  // start half a tile behind warpgroup 0
+      if (j == 0 && wg == 1) asm volatile("bar.sync 1, 512;" ::: "memory");  // start half a tile behind group 0
       {
         float la, lb;
         unpack_f2(l2, la, lb);
@@ -263,7 +287,7 @@ __global__ void __launch_bounds__(384, 1) attention2_kernel(const __grid_constan
       const uint64_t off2 = pack_f2(nmoff, nmoff);
       uint8_t* sPb = sPq + jp * Cfg::P_TILE_BYTES;
 #pragma unroll
-      for (int c0 = 0; c0 < BKV; c0 += 8) {
+      for (int c0 = 0; c0 < HC; c0 += 8) {
         uint32_t pk[4];
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
@@ -276,9 +300,10 @@ __global__ void __launch_bounds__(384, 1) attention2_kernel(const __grid_constan
           l2 = add_f2(l2, pack_f2(e0, e1));
           pk[i >> 1] = pack_h2(e0, e1);
         }
-        const uint32_t off = (c0 >> 6) * 16384 + ((((c0 & 63) >> 3) ^ (row & 7)) << 4);
+        const int c = half * HC + c0;  // column inside the BKV-wide P tile
+        const uint32_t off = (c >> 6) * 16384 + ((((c & 63) >> 3) ^ (row & 7)) << 4);
         *reinterpret_cast<uint4*>(sPb + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        if (c0 == BKV / 2 - 8 && j == 0 && wg == 0) asm volatile("bar.arrive 1, 256;" ::: "memory");
+        if (c0 == HC / 2 - 8 && j == 0 && wg == 0) asm volatile("bar.arrive 1, 512;" ::: "memory");
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -286,30 +311,29 @@ __global__ void __launch_bounds__(384, 1) attention2_kernel(const __grid_constan
       if (lane == 0) mbar_arrive(&p_full[wg]);
     }
 
-    // ---- epilogue: O / l -> fp16
-    mbar_wait(&o_full_q[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);
-    tc_fence_after();
+    // ---- epilogue: O / l -> fp16; the two threads of a row add their half-row sums and split the head dim
     float la, lb;
     unpack_f2(l2, la, lb);
-    const float inv = 1.f / (la + lb);
+    const uint32_t xp = nkv & 1;
+    xmine[xp * 2] = la + lb;
+    named_bar_sync256(bar_id);
+    const float inv = 1.f / (la + lb + xpeer[xp * 2]);
+    mbar_wait(&o_full_q[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);
+    tc_fence_after();
     const int q = q0 + wg * 128 + row;
     __half* orow = p.out + (static_cast<long long>(b) * p.Tq + q) * p.ld_out + head * D;
-#pragma unroll
-    for (int c0 = 0; c0 < DK; c0 += 16) {
-      uint32_t o[16];
-      tmem_ld_x16(t_o + c0, o);
+    constexpr int N8 = D / 8;
+    const int c8_lo = half == 0 ? 0 : (N8 + 1) / 2, c8_hi = half == 0 ? (N8 + 1) / 2 : N8;
+    for (int c8 = c8_lo; c8 < c8_hi; ++c8) {
+      uint32_t o[8];
+      tmem_ld_x8(t_o + c8 * 8, o);
       tmem_wait_ld();
       if (q < p.Tq) {
-#pragma unroll
-        for (int i = 0; i < 16; i += 8) {
-          if (c0 + i < D) {
-            *reinterpret_cast<uint4*>(orow + c0 + i) =
-                make_uint4(pack_h2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv),
-                           pack_h2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv),
-                           pack_h2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv),
-                           pack_h2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv));
-          }
-        }
+        *reinterpret_cast<uint4*>(orow + c8 * 8) =
+            make_uint4(pack_h2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv),
+                       pack_h2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv),
+                       pack_h2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv),
+                       pack_h2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv));
       }
     }
   }
