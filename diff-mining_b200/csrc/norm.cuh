@@ -6,6 +6,8 @@
 // (reference: /root/reference/diffmining/typicality/dift.py:141-165) is never materialised un-normalised;
 // groups may straddle the concat boundary.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "ptx.cuh"
 
 namespace dm {
@@ -154,6 +156,140 @@ __global__ void __launch_bounds__(384) gn_apply_kernel(NormSrc s0, NormSrc s1, i
   long long ps;
   const __half* base = norm_src_ptr(s0, s1, c, ps);
   base += static_cast<long long>(n) * HW * ps;
+  __half* obase = out + static_cast<long long>(n) * HW * C + c;
+  auto apply = [&](const uint4& u, int px) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      float y0 = f.x * sa[2 * i] + sb[2 * i], y1 = f.y * sa[2 * i + 1] + sb[2 * i + 1];
+      if (silu) { y0 = silu_fast(y0); y1 = silu_fast(y1); }
+      pk[i] = pack_h2(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(obase + static_cast<long long>(px) * C) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  };
+  int px = p0 + r;
+  for (; px + 3 * R < p1; px += 4 * R) {
+    const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(base + px * ps));
+    const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(base + (px + R) * ps));
+    const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(base + (px + 2 * R) * ps));
+    const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(base + (px + 3 * R) * ps));
+    apply(u0, px); apply(u1, px + R); apply(u2, px + 2 * R); apply(u3, px + 3 * R);
+  }
+  for (; px < p1; px += R) apply(__ldg(reinterpret_cast<const uint4*>(base + px * ps)), px);
+}
+
+// Fused GroupNorm for images that fit in L2 (every U-Net activation): ONE kernel, one thread-block cluster per image.
+// grid (CL, Nimg), cluster (CL, 1, 1): CTA `rank` owns pixels [rank*px_per, (rank+1)*px_per) of image blockIdx.y.
+//   pass 1  per-thread channel sums over the CTA's pixel slice (same thread map as gn_stats_kernel), folded to 32
+//           group partials in shared memory
+//   cluster.sync, every CTA reads the CL partials of its image through distributed shared memory IN RANK ORDER
+//           (deterministic: fixed slices, fixed fold, fixed order -- and the geometry depends on (HW, C) only, so an
+//           image's statistics do not depend on the batch it is in)
+//   pass 2  the slice is read again -- an L2 hit, it was streamed a few microseconds ago -- normalised (+SiLU) and
+//           written.  HBM traffic = 1 read + 1 write of the activation (the two-kernel path reads it twice).
+__global__ void __launch_bounds__(384) gn_fused_kernel(NormSrc s0, NormSrc s1, int HW, int cpg, int px_per, int VT, int R,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float eps, int silu, __half* __restrict__ out) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ float sm_gn[];  // [2][R*VT*8] per-thread channel sums
+  __shared__ float part[64];        // this CTA's (sum, sumsq) per group
+  __shared__ float stat[64];        // mean[32], rstd[32]
+  const int n = blockIdx.y;
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int CL = static_cast<int>(cluster.num_blocks());
+  const int C = s0.C + s1.C;
+  const int nthr = VT * R;
+  float* sm_a = sm_gn;
+  float* sm_q = sm_gn + nthr * 8;
+  const int r = threadIdx.x / VT, vt = threadIdx.x % VT;
+  const int p0 = rank * px_per, p1 = min(HW, p0 + px_per);
+  const bool active = threadIdx.x < nthr;
+  long long ps = 0;
+  const __half* base = nullptr;
+  if (active) {
+    base = norm_src_ptr(s0, s1, vt << 3, ps);
+    base += static_cast<long long>(n) * HW * ps;
+  }
+  float a[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a[i] = 0.f; q[i] = 0.f; }
+  if (active) {
+    auto acc = [&](const uint4& u) {
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        a[2 * i] += f.x; q[2 * i] += f.x * f.x;
+        a[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+      }
+    };
+    int px = p0 + r;
+    for (; px + 7 * R < p1; px += 8 * R) {
+      uint4 u[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(base + (px + k * R) * ps));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc(u[k]);
+    }
+    for (; px < p1; px += R) acc(__ldg(reinterpret_cast<const uint4*>(base + px * ps)));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sm_a[threadIdx.x * 8 + i] = a[i];  // index = r*C + channel
+      sm_q[threadIdx.x * 8 + i] = q[i];
+    }
+  }
+  __syncthreads();
+  {
+    // group g folded by 8 consecutive lanes (k = lane & 7), then a fixed xor tree
+    const int g = threadIdx.x >> 3, k = threadIdx.x & 7;
+    float gs = 0.f, gq = 0.f;
+    if (g < 32) {
+      for (int rr = 0; rr < R; ++rr)
+        for (int cc = k; cc < cpg; cc += 8) {
+          gs += sm_a[rr * C + g * cpg + cc];
+          gq += sm_q[rr * C + g * cpg + cc];
+        }
+    }
+    if (threadIdx.x < 256) {  // whole warps (blockDim >= 256 is guaranteed by the launcher)
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        gs += __shfl_xor_sync(0xffffffffu, gs, o);
+        gq += __shfl_xor_sync(0xffffffffu, gq, o);
+      }
+      if (k == 0) {
+        part[2 * g] = gs;
+        part[2 * g + 1] = gq;
+      }
+    }
+  }
+  cluster.sync();
+  if (threadIdx.x < 32) {
+    float s = 0.f, qq = 0.f;
+    for (int c = 0; c < CL; ++c) {
+      const float* rp = cluster.map_shared_rank(part, c);
+      s += rp[2 * threadIdx.x];
+      qq += rp[2 * threadIdx.x + 1];
+    }
+    const float cnt = static_cast<float>(HW) * cpg;
+    const float mean = s / cnt;
+    const float var = fmaxf(qq / cnt - mean * mean, 0.f);
+    stat[threadIdx.x] = mean;
+    stat[32 + threadIdx.x] = rsqrtf(var + eps);
+  }
+  cluster.sync();  // also keeps every CTA's `part` alive until all remote reads are done
+  if (!active) return;
+  const int c = vt << 3;
+  float sa[8], sb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = (c + i) / cpg;
+    const float sc = gamma[c + i] * stat[32 + g];
+    sa[i] = sc;
+    sb[i] = beta[c + i] - stat[g] * sc;
+  }
   __half* obase = out + static_cast<long long>(n) * HW * C + c;
   auto apply = [&](const uint4& u, int px) {
     const __half2* h = reinterpret_cast<const __half2*>(&u);

@@ -106,6 +106,7 @@ struct GnDesc {
   __half* out = nullptr;     // dense [Nimg, HW, C0+C1]
 };
 int gn_splits(int Nimg, int HW);
+int gn_launch_count(int HW, int C);  // kernels gn_launch() issues for this shape (1 = cluster-fused, 2 = stats + apply)
 void gn_launch(const GnDesc& d, cudaStream_t s);
 void layernorm_launch(const __half* x, long long ld_x, const float* gamma, const float* beta, float eps, long long rows,
                       int C, __half* out, long long ld_out, cudaStream_t s);

@@ -66,7 +66,7 @@ struct Builder {
                    static_cast<size_t>(2) * x0.N * C <= e.gn_ab_floats && static_cast<size_t>(x0.N) <= e.gn_ticket_count,
                "GroupNorm scratch too small");
       d.out = hp(o);
-      push(Step{[d](cudaStream_t s) { gn_launch(d, s); }, kStepOther, 0, 2, name});
+      push(Step{[d](cudaStream_t s) { gn_launch(d, s); }, kStepOther, 0, gn_launch_count(d.HW, C), name});
     }
     return o;
   }
