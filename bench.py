@@ -41,8 +41,14 @@ IMAGES_PER_STEP = 16
 N_DRAWS = 32
 IMG = 512
 LAT = IMG // 8
-MICRO_BATCH = 32
+MICRO_BATCH = 56  # cap; the engine balances: 1024 forwards -> 19 micro-batches of 54 / 52 (fills 148 SMs at every level)
 FLOP_PER_SAMPLE = 64 * 803.3e9 + 1116.7e9
+
+
+def balanced_microbatch(total, cap, n_cond=2):
+    """the engine's micro-batch size (abi_engine.cu dm_typicality): fewest batches under the cap, equal sizes"""
+    n_mb = -(-total // cap)
+    return -(-(-(-total // n_mb)) // n_cond) * n_cond
 
 
 def load_peaks():
@@ -263,7 +269,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "configs[1]: per GPU 16x 512x512 synthetic RGB, 32 (eps,t) draws, cond+uncond = 1024 U-Net forwards "
                                    "@64x64 + 16 VAE encodes per step; synthetic seeded SD-1.5 weights (859.5M U-Net, 34.2M VAE enc)",
-                       "images_per_gpu_step": IMAGES_PER_STEP, "mc_samples": N_DRAWS, "n_cond": 2, "micro_batch_forwards": MICRO_BATCH,
+                       "images_per_gpu_step": IMAGES_PER_STEP, "mc_samples": N_DRAWS, "n_cond": 2, "micro_batch_forwards": balanced_microbatch(IMAGES_PER_STEP * N_DRAWS * 2, MICRO_BATCH),
                        "l2": "inputs larger than L2: each micro-batch streams 1.72 GB of weights + >1 GB of activations through a 126 MB L2; no explicit flush",
                        "parallelism": f"dp{world} (image sharding, one all-gather of T maps)"},
             "clocks": clk, "gpu_launches": int(launches),
@@ -273,7 +279,7 @@ def run_ours(args):
     if rank == 0:
         # ---- roofline of the dominant kernel: every igemm launch of one 32-forward micro-batch, events per launch
         pk = load_peaks()
-        pr = eng.profile_unet(MICRO_BATCH, LAT, LAT, iters=3)
+        pr = eng.profile_unet(balanced_microbatch(IMAGES_PER_STEP * N_DRAWS * 2, MICRO_BATCH), LAT, LAT, iters=3)
         n_ig = None
         ach = pr["flops_igemm"] / (pr["ms_igemm"] * 1e-3) / 1e12
         traffic = None

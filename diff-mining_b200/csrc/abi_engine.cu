@@ -233,7 +233,11 @@ extern "C" int dm_typicality(dm_engine* h, const float* x0, const float* noise, 
     DM_CUDA(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     const int HW = hh * ww;
     __half* grid = grid_out ? static_cast<__half*>(grid_out) : ensure_grid(h, static_cast<size_t>(F) * 4 * HW);
-    const int Bf = static_cast<int>(std::min<long long>(F, max_forwards > 0 ? max_forwards : kDefaultMaxForwards));
+    // balanced micro-batches: as few as the cap allows, equal sizes (whole (eps,t) draws: multiples of n_cond), so no
+    // small remainder batch under-fills the 148 SMs
+    const long long cap = std::max<long long>(n_cond, max_forwards > 0 ? max_forwards : kDefaultMaxForwards);
+    const long long n_mb = (F + cap - 1) / cap;
+    const int Bf = static_cast<int>(((F + n_mb - 1) / n_mb + n_cond - 1) / n_cond * n_cond);
     for (long long f0 = 0; f0 < F; f0 += Bf) {
       const int nb = static_cast<int>(std::min<long long>(Bf, F - f0));
       Plan* p = unet_microbatch(e, kPlanUnet, 0, x0, dev + f0, noise, dev + F + f0, reinterpret_cast<const long long*>(t),
