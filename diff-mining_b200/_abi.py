@@ -41,6 +41,7 @@ SIGNATURES = {
     "dm_op_attention": (I, [P, P, P, L, L, L, L, L, L, I, I, I, I, I, I, P, P, L, P]),
     "dm_op_groupnorm": (I, [P, P, I, I, I, I, P, P, F, I, P, P]),
     "dm_op_layernorm": (I, [P, L, I, P, P, F, P, P]),
+    "dm_op_set_variant": (I, [ctypes.c_char_p, I]),
 }
 
 _lib = None

@@ -140,6 +140,13 @@ extern "C" int dm_op_groupnorm(const void* x, const void* x2, int N, int HW, int
   });
 }
 
+extern "C" int dm_op_set_variant(const char* name, int value) {
+  return abi_guard([&] {
+    DM_CHECK(name != nullptr, "dm_op_set_variant: null name");
+    set_variant(name, value);
+  });
+}
+
 extern "C" int dm_op_layernorm(const void* x, int64_t rows, int C, const float* gamma, const float* beta, float eps,
                                void* out, void* stream) {
   return abi_guard([&] {

@@ -63,10 +63,14 @@ struct IgParams {
   int out_f32, geglu, act_silu;
 };
 
-template <int BN, bool DIRECT>
+// CG = CTAs per tile: 1, or 2 = a CTA pair (cta_group::2) computing a 256 x BN tile with each CTA holding its 128
+// rows of A and HALF of the B tile, which cuts the per-SM shared-memory operand traffic and the L2 -> SM weight
+// traffic by the B half.
+template <int BN, bool DIRECT, int CG = 1>
 struct IgCfg {
   static constexpr int A_BYTES = IG_BM * IG_BK * 2;
-  static constexpr int B_BYTES = BN * IG_BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * IG_BK * 2;
+  static_assert(CG == 1 || (CG == 2 && !DIRECT && BN % 32 == 0), "CTA pairs: staged epilogue, BN multiple of 32");
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NBG = DIRECT ? 0 : (BN >= 256 ? 2 : 4);  // chunk buffers per epilogue warpgroup
   static constexpr int LOOKAHEAD = NBG >= 4 ? 2 : 1;             // residual prefetch distance (chunks)
@@ -138,9 +142,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int BN, bool DIRECT>
+template <int BN, bool DIRECT, int CG>
 __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_constant__ IgMaps maps, const IgParams p) {
-  using Cfg = IgCfg<BN, DIRECT>;
+  using Cfg = IgCfg<BN, DIRECT, CG>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NBG = Cfg::NBG;
   extern __shared__ __align__(1024) uint8_t smem[];  // 128B-swizzled tiles need 1024-byte alignment
@@ -159,16 +163,19 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int unit = static_cast<int>(blockIdx.x) / CG;     // tile-processing unit: a CTA, or a CTA pair
+  const int nunits = static_cast<int>(gridDim.x) / CG;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full[i], 1);
+      mbar_init(&full[i], 1);   // CG == 2: only the leader's is used (both CTAs' loads complete_tx on it)
       mbar_init(&empty[i], 1);
     }
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 8);
-    mbar_init(&tempty[1], 8);
+    mbar_init(&tempty[0], 8 * CG);  // CG == 2: the leader's collects the epilogue warps of both CTAs
+    mbar_init(&tempty[1], 8 * CG);
     for (int i = 0; i < 8; ++i) mbar_init(&rfull[i], 1);
     fence_barrier_init();
     tma_prefetch_desc(&maps.a[0]);
@@ -176,22 +183,30 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
     if constexpr (!DIRECT) tma_prefetch_desc(&maps.c);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  // tiles are (m-unit, n-tile): an m-unit is CG consecutive 128-row M-tiles (an odd tail unit has a dummy second
+  // tile whose loads are zero-filled and whose stores are clipped by the tensor maps)
+  const int num_tiles = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles, ntile = tile % p.n_tiles;
+      for (int tile = unit; tile < num_tiles; tile += nunits) {
+        const int mt = (tile / p.n_tiles) * CG + cta_rank, ntile = tile % p.n_tiles;
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
         const int x0 = tx << p.wt_log, y0 = ty << p.ht_log, n0 = tn << p.nt_log;
         int kit = 0;
@@ -200,10 +215,19 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           const CUtensorMap* am = &maps.a[sg.src];
           for (int c = 0; c < sg.nchunks; ++c, ++kit) {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-            tma_load_4d(smA + stage * Cfg::A_BYTES, am, &full[stage], sg.chan0 + c * IG_BK, x0 + sg.dx, y0 + sg.dy,
-                        n0 + sg.dn);
-            tma_load_2d(smB + stage * Cfg::B_BYTES, &maps.b, &full[stage], kit * IG_BK, ntile * BN);
+            if constexpr (CG == 2) {
+              // the leader arms its barrier for the bytes of BOTH CTAs; each CTA loads its A rows and its B half
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+              tma_load_4d_pair(smA + stage * Cfg::A_BYTES, am, &full[stage], sg.chan0 + c * IG_BK, x0 + sg.dx,
+                               y0 + sg.dy, n0 + sg.dn);
+              tma_load_2d_pair(smB + stage * Cfg::B_BYTES, &maps.b, &full[stage], kit * IG_BK,
+                               ntile * BN + cta_rank * (BN / 2));
+            } else {
+              mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+              tma_load_4d(smA + stage * Cfg::A_BYTES, am, &full[stage], sg.chan0 + c * IG_BK, x0 + sg.dx, y0 + sg.dy,
+                          n0 + sg.dn);
+              tma_load_2d(smB + stage * Cfg::B_BYTES, &maps.b, &full[stage], kit * IG_BK, ntile * BN);
+            }
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -214,12 +238,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN, false, 128 * CG);
       int stage = 0;
       uint32_t phase = 0;
       int lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      for (int tile = unit; tile < num_tiles; tile += nunits, ++lt) {
         const int acc = lt & 1;
         const uint32_t acc_phase = (lt >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -233,15 +257,18 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
 #pragma unroll
           for (int k = 0; k < IG_BK / 16; ++k) {
             // advance 16 fp16 = 32 B along K inside the 128-B swizzle row: +2 in (addr>>4) units
-            umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kit | k) != 0 ? 1u : 0u);
+            if constexpr (CG == 2) umma_f16_pair(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kit | k) != 0 ? 1u : 0u);
+            else umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kit | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);
+          if constexpr (CG == 2) umma_commit_pair(&empty[stage]);
+          else umma_commit(&empty[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);
+        if constexpr (CG == 2) umma_commit_pair(&tfull[acc]);
+        else umma_commit(&tfull[acc]);
       }
     }
   } else {
@@ -253,7 +280,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
     if constexpr (DIRECT) {
       constexpr int CH = (BN % 32 == 0) ? 32 : 16;
       int lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      for (int tile = unit; tile < num_tiles; tile += nunits, ++lt) {
         const int acc = lt & 1;
         const uint32_t acc_phase = (lt >> 1) & 1;
         const int mt = tile / p.n_tiles, ntile = tile % p.n_tiles;
@@ -370,7 +397,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
       auto first_c = [&](int lt_) { return (eg ^ (lt_ * nchunk)) & 1; };
       auto settle = [&](It& it) {  // skip tiles in which this group owns no chunk
         while (it.tile < num_tiles && it.c >= nchunk) {
-          it.tile += gridDim.x;
+          it.tile += nunits;
           it.lt += 1;
           it.c = first_c(it.lt);
         }
@@ -380,12 +407,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         settle(it);
       };
       auto coords = [&](const It& it, int& col, int& x0, int& y0, int& n0) {
-        const int mt = it.tile / p.n_tiles, ntile = it.tile % p.n_tiles;
+        const int mt = (it.tile / p.n_tiles) * CG + cta_rank, ntile = it.tile % p.n_tiles;
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
         x0 = tx << p.wt_log; y0 = ty << p.ht_log; n0 = tn << p.nt_log;
         col = ntile * out_tile_cols + it.c * IG_CW;
       };
-      It pf{static_cast<int>(blockIdx.x), 0, first_c(0)};  // residual prefetch cursor (leader only)
+      It pf{unit, 0, first_c(0)};  // residual prefetch cursor (leader thread only)
       settle(pf);
       int pf_k = 0;
       auto prefetch_one = [&]() {
@@ -406,10 +433,11 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
 
       int k = 0;  // chunks processed by this warpgroup
       int lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      for (int tile = unit; tile < num_tiles; tile += nunits, ++lt) {
         const int acc = lt & 1;
         const uint32_t acc_phase = (lt >> 1) & 1;
         const int ntile = tile % p.n_tiles;
+        const int mt = (tile / p.n_tiles) * CG + cta_rank;  // this CTA's M-tile of the unit
         if (p.bias) {
           for (int i = gtid; i < BN; i += 128) {
             const int col = ntile * BN + i;
@@ -419,7 +447,6 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         }
         const __half* rb = nullptr;
         if (p.rowbias) {
-          const int mt = tile / p.n_tiles;
           const int tn = mt / (p.tiles_x * p.tiles_y);
           int n = (tn << p.nt_log) + (r >> (p.wt_log + p.ht_log));
           n = n < p.Nimg ? n : p.Nimg - 1;
@@ -487,7 +514,10 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           if (c + 2 >= nchunk) {  // last TMEM read of this tile by this warp: hand the accumulator back
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) {
+              if constexpr (CG == 2) mbar_arrive_cluster(&tempty[acc], 0);  // the issuer lives in the leader CTA
+              else mbar_arrive(&tempty[acc]);
+            }
           }
           if (has_res) {
             mbar_wait(&rf[b], (k / NBG) & 1);
@@ -511,7 +541,6 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           }
           named_bar_sync(bar_id, 128);
           if (leader) {
-            const int mt = tile / p.n_tiles;
             const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
             tma_store_4d(&maps.c, ring + b * IG_CHUNK_BYTES, ntile * out_tile_cols + c * IG_CW, tx << p.wt_log,
                          ty << p.ht_log, tn << p.nt_log);
@@ -522,7 +551,10 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         if (c_first >= nchunk) {  // this group owns no chunk of the tile: still release the accumulator
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_cluster(&tempty[acc], 0);
+            else mbar_arrive(&tempty[acc]);
+          }
         }
       }
       if (leader) tma_store_wait_all();
@@ -530,10 +562,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // nobody leaves while its peer may still signal it or read its operands
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 

@@ -52,6 +52,20 @@ static void make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t*
   DM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
 }
 
+// ------------------------------------------------------------------ kernel-variant switches
+static int g_igemm_pair = -1, g_gn_fused = -1;
+static int env_or(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+static int variant_igemm_pair() { return g_igemm_pair >= 0 ? g_igemm_pair : env_or("DM_IGEMM_PAIR", 1); }
+static int variant_gn_fused() { return g_gn_fused >= 0 ? g_gn_fused : env_or("DM_GN_FUSED", 1); }
+void set_variant(const std::string& name, int value) {
+  if (name == "igemm_pair") g_igemm_pair = value;
+  else if (name == "gn_fused") g_gn_fused = value;
+  else DM_CHECK(false, "unknown kernel variant '" + name + "'");
+}
+
 // ------------------------------------------------------------------ igemm
 void seg_conv3x3(IgemmDesc& d, int Cin_total, int C0) {
   d.nseg = 0;
@@ -144,6 +158,14 @@ IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms) {
   DM_CHECK(d.out != nullptr && d.ld_out % 8 == 0, "igemm: bad output");
   // staged epilogue (TMA store / residual prefetch) unless the output is fp32 or the N-tile is narrower than a chunk
   op.direct = (d.out_f32 || op.bn < 32) ? 1 : 0;
+  // CTA pairs (cta_group::2, 256-row tiles) when there is enough work to keep every SM pair busy
+  const int pair_mode = variant_igemm_pair();
+  // (pair_mode 2 = use pairs whenever the tile shape allows it: unit tests)
+  op.cg = (pair_mode && !op.direct && op.bn >= 128 &&
+           (pair_mode == 2 || d.cg == 2 ||
+            (d.cg == 0 && p.m_tiles >= 2 && kit >= 16 &&  // short-K layers are epilogue-bound: pairs only couple them
+             static_cast<long long>((p.m_tiles + 1) / 2) * p.n_tiles >= num_sms / 2)))
+              ? 2 : 1;
   DM_CHECK(!d.geglu || (op.bn % 64 == 0 && !op.direct), "igemm: GEGLU needs an N-tile that is a multiple of 64");
   DM_CHECK(!d.geglu || (!d.residual && !d.rowbias && !d.act_silu), "igemm: GEGLU excludes the other epilogue options");
   if (!op.direct) {
@@ -176,46 +198,71 @@ IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms) {
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.N)};
     const uint64_t st[1] = {static_cast<uint64_t>(d.w_ld ? d.w_ld : d.K) * 2};
-    const uint32_t box[2] = {64, static_cast<uint32_t>(op.bn)};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(op.bn / op.cg)};  // a CTA of a pair loads half of the B tile
     make_tmap(&op.maps.b, d.Wt, 2, dims, st, box);
   }
-  const int tiles = p.m_tiles * p.n_tiles;
-  op.grid = std::min(tiles, num_sms);
+  const int tiles = ((p.m_tiles + op.cg - 1) / op.cg) * p.n_tiles;
+  op.grid = std::min(tiles, num_sms / op.cg) * op.cg;
   op.flops = 2.0 * d.Nimg * d.H * d.W * static_cast<double>(d.N) * d.K;
   return op;
 }
 
-template <int BN, bool DIRECT>
+template <int BN, bool DIRECT, int CG>
 static void igemm_launch_bn(const IgemmOp& op, cudaStream_t s) {
   static bool configured = false;
-  using Cfg = IgCfg<BN, DIRECT>;
+  using Cfg = IgCfg<BN, DIRECT, CG>;
   if (!configured) {
-    DM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    DM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, DIRECT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  igemm_kernel<BN, DIRECT><<<op.grid, IG_THREADS, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
-  DM_CUDA(cudaGetLastError());
+  if (CG == 1) {
+    igemm_kernel<BN, DIRECT, CG><<<op.grid, IG_THREADS, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
+    DM_CUDA(cudaGetLastError());
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(op.grid, 1, 1);
+    cfg.blockDim = dim3(IG_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DM_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<BN, DIRECT, CG>, op.maps, op.p));
+  }
 }
 
 void igemm_launch(const IgemmOp& op, cudaStream_t s) {
   if (op.direct) {
     switch (op.bn) {
-      case 256: igemm_launch_bn<256, true>(op, s); break;
-      case 160: igemm_launch_bn<160, true>(op, s); break;
-      case 128: igemm_launch_bn<128, true>(op, s); break;
-      case 64: igemm_launch_bn<64, true>(op, s); break;
-      case 32: igemm_launch_bn<32, true>(op, s); break;
-      case 16: igemm_launch_bn<16, true>(op, s); break;
+      case 256: igemm_launch_bn<256, true, 1>(op, s); break;
+      case 160: igemm_launch_bn<160, true, 1>(op, s); break;
+      case 128: igemm_launch_bn<128, true, 1>(op, s); break;
+      case 64: igemm_launch_bn<64, true, 1>(op, s); break;
+      case 32: igemm_launch_bn<32, true, 1>(op, s); break;
+      case 16: igemm_launch_bn<16, true, 1>(op, s); break;
       default: DM_CHECK(false, "igemm: unsupported BN " + std::to_string(op.bn) + " for the direct epilogue");
     }
     return;
   }
+  if (op.cg == 2) {
+    switch (op.bn) {
+      case 256: igemm_launch_bn<256, false, 2>(op, s); break;
+      case 160: igemm_launch_bn<160, false, 2>(op, s); break;
+      case 128: igemm_launch_bn<128, false, 2>(op, s); break;
+      default: DM_CHECK(false, "igemm: unsupported BN " + std::to_string(op.bn) + " for CTA pairs");
+    }
+    return;
+  }
   switch (op.bn) {
-    case 256: igemm_launch_bn<256, false>(op, s); break;
-    case 160: igemm_launch_bn<160, false>(op, s); break;
-    case 128: igemm_launch_bn<128, false>(op, s); break;
-    case 64: igemm_launch_bn<64, false>(op, s); break;
-    case 32: igemm_launch_bn<32, false>(op, s); break;
+    case 256: igemm_launch_bn<256, false, 1>(op, s); break;
+    case 160: igemm_launch_bn<160, false, 1>(op, s); break;
+    case 128: igemm_launch_bn<128, false, 1>(op, s); break;
+    case 64: igemm_launch_bn<64, false, 1>(op, s); break;
+    case 32: igemm_launch_bn<32, false, 1>(op, s); break;
     default: DM_CHECK(false, "igemm: unsupported BN " + std::to_string(op.bn));
   }
 }
@@ -317,8 +364,7 @@ int gn_splits(int Nimg, int HW) {
 }
 
 static bool gn_use_fused(int HW, int C) {
-  static const int fused_mode = [] { const char* e = getenv("DM_GN_FUSED"); return e ? atoi(e) : 1; }();
-  return fused_mode && static_cast<long long>(HW) * C * 2 <= (12ll << 20);
+  return variant_gn_fused() && static_cast<long long>(HW) * C * 2 <= (12ll << 20);
 }
 int gn_launch_count(int HW, int C) { return gn_use_fused(HW, C) ? 1 : 2; }
 

@@ -54,6 +54,7 @@ struct IgemmDesc {
   long long ld_out = 0;
   int out_f32 = 0, geglu = 0, act_silu = 0;
   int bn = 0;  // 0 = choose
+  int cg = 0;  // CTAs per tile: 0 = choose, 1 = single CTA, 2 = CTA pair (cta_group::2)
 };
 
 struct IgemmOp {
@@ -61,9 +62,11 @@ struct IgemmOp {
   IgParams p;
   int bn = 0, grid = 0;
   int direct = 0;  // 1 = plain global-store epilogue (fp32 output or N-tile < 32 columns)
+  int cg = 1;      // CTAs per tile (2 = CTA pair)
   double flops = 0;
 };
 
+void set_variant(const std::string& name, int value);  // "igemm_pair" / "gn_fused": 0, 1, or -1 = default
 IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms);
 void igemm_launch(const IgemmOp& op, cudaStream_t s);
 // convenience segment builders

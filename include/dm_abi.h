@@ -118,6 +118,11 @@ int dm_op_groupnorm(const void* x, const void* x2, int N, int HW, int C0, int C1
                     float eps, int silu, void* out, void* stream);
 int dm_op_layernorm(const void* x, int64_t rows, int C, const float* gamma, const float* beta, float eps, void* out,
                     void* stream);
+/* kernel-variant switches for tests / A-B timing (affect ops prepared afterwards; -1 = built-in default):
+ *   igemm_pair  1 = CTA pairs (tcgen05 cta_group::2, 256-row tiles) where the problem is large enough, 0 = never,
+ *               2 = wherever the tile shape allows (N-tile >= 128, fp16 output)
+ *   gn_fused    1 = cluster-fused single-pass GroupNorm for images that fit in L2, 0 = two-kernel path */
+int dm_op_set_variant(const char* name, int value);
 
 #ifdef __cplusplus
 }

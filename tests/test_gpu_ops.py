@@ -103,6 +103,38 @@ def test_conv_igemm(lib, case):
     assert max_rel(out, ref) < (1e-5 if f32 else 2.5e-3)  # fp16 output: ~2 ulp of the output scale
 
 
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[5] >= 128 and not c[13] and c[14] in (0, 128, 160, 256)],
+                         ids=lambda c: "-".join(map(str, c)))
+def test_conv_igemm_cta_pairs(lib, case):
+    """same cases on the cta_group::2 path (256-row tiles over a CTA pair), forced even for tiny problems: odd M-tile
+    counts (dummy second tile), ragged tiles, every epilogue option"""
+    check(lib, lib.dm_op_set_variant(b"igemm_pair", 2))
+    try:
+        test_conv_igemm(lib, case)
+    finally:
+        check(lib, lib.dm_op_set_variant(b"igemm_pair", -1))
+
+
+def test_groupnorm_two_kernel_path_matches_fused(lib):
+    """the cluster-fused GroupNorm and the stats + apply path agree (both deterministic)"""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    N, HW, C = 3, 1024, 640
+    x = torch.randn(N, HW, C, device="cuda", generator=g).half()
+    gamma = torch.randn(C, device="cuda", generator=g)
+    beta = torch.randn(C, device="cuda", generator=g)
+    outs = []
+    for mode in (1, 0):
+        check(lib, lib.dm_op_set_variant(b"gn_fused", mode))
+        out = torch.empty_like(x)
+        check(lib, lib.dm_op_groupnorm(ptr(x), None, N, HW, C, 0, ptr(gamma), ptr(beta), 1e-5, 1, ptr(out), stream()))
+        torch.cuda.synchronize()
+        outs.append(out)
+    check(lib, lib.dm_op_set_variant(b"gn_fused", -1))
+    ref = F.silu(F.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, 1e-5)).permute(0, 2, 1)
+    assert max_rel(outs[0], ref) < 2e-3 and max_rel(outs[1], ref) < 2e-3
+    assert max_rel(outs[0], outs[1]) < 1e-3
+
+
 ATTN_CASES = [
     # B, Tq, Tk, D, cross
     (1, 128, 128, 40, 0), (2, 4096, 4096, 40, 0), (2, 1024, 1024, 80, 0), (2, 256, 256, 160, 0), (3, 64, 64, 160, 0),
