@@ -222,4 +222,138 @@ __global__ void __launch_bounds__(128, 1) attention_kernel(const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Cross-attention against a short key set (the 77 CLIP tokens): one KV tile, no online softmax.  The op is bound by
+// reading Q and writing O, so the kernel is built for occupancy and a short dependency chain instead of for the
+// tensor pipe:  S = Q K^T lands in 80 TMEM columns, thread r turns row r into probabilities in registers and
+// writes them back as packed fp16 INTO THE SAME TMEM COLUMNS, and O = P V takes its A operand straight from tensor
+// memory (tcgen05.mma with A in TMEM) -- no shared-memory round trip for P, 128 TMEM columns and 36 KB of shared
+// memory per CTA at head_dim 40, so four CTAs are co-resident per SM and hide each other's TMA / MMA latency.
+template <int D>
+struct XAttnCfg {
+  static constexpr int DK = (D + 15) / 16 * 16;
+  static constexpr int NCH = (D + 63) / 64;
+  static constexpr int TK = 80;                       // key rows staged / UMMA N (>= 77, multiple of 16)
+  static constexpr int Q_BYTES = NCH * 128 * 128;
+  static constexpr int KV_BYTES = NCH * TK * 128;
+  static constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_BYTES + 64;
+  static constexpr int O_COL = TK;                    // S (fp32) / P (fp16, first TK/2 columns) at [0, TK)
+  static constexpr int TMEM_COLS = (TK + DK <= 128) ? 128 : 256;
+};
+
+template <int D>
+__global__ void __launch_bounds__(128) xattention_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
+  using Cfg = XAttnCfg<D>;
+  constexpr int DK = Cfg::DK, NCH = Cfg::NCH, TK = Cfg::TK;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + Cfg::KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + Cfg::KV_BYTES);
+  uint64_t *bar_qk = bars, *bar_v = bars + 1, *bar_s = bars + 2, *bar_o = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
+  const int kvb = p.kv_index ? p.kv_index[b] : b;
+
+  if (tid == 0) {
+    mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(bar_qk, Cfg::Q_BYTES + Cfg::KV_BYTES);
+    for (int c = 0; c < NCH; ++c) tma_load_4d(sQ + c * 16384, &maps.q, bar_qk, c * 64, head, q0, b);
+    for (int c = 0; c < NCH; ++c) tma_load_4d(sK + c * TK * 128, &maps.k, bar_qk, c * 64, head, 0, kvb);
+    mbar_arrive_expect_tx(bar_v, Cfg::KV_BYTES);
+    for (int c = 0; c < NCH; ++c) tma_load_4d(sV + c * TK * 128, &maps.v, bar_v, c * 64, head, 0, kvb);
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);  // this thread's lane quarter
+
+  if (tid == 0) {
+    constexpr uint32_t idesc_s = umma_idesc_f16(TK, false);
+    mbar_wait(bar_qk, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int ks = 0; ks < DK / 16; ++ks) {
+      const uint64_t ad = umma_desc_kmajor_sw128(smem_u32(sQ + (ks >> 2) * 16384)) + 2 * (ks & 3);
+      const uint64_t bd = umma_desc_kmajor_sw128(smem_u32(sK + (ks >> 2) * TK * 128)) + 2 * (ks & 3);
+      umma_f16(tmem_base, ad, bd, idesc_s, ks != 0 ? 1u : 0u);
+    }
+    umma_commit(bar_s);
+  }
+  mbar_wait(bar_s, 0);
+  tc_fence_after();
+  // ---- softmax of row `tid` over the Tk valid keys, in registers
+  uint32_t raw[TK];
+#pragma unroll
+  for (int c0 = 0; c0 < TK; c0 += 16) tmem_ld_x16(t_row + c0, raw + c0);
+  tmem_wait_ld();
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < TK; ++i) {
+    if (i >= p.Tk) raw[i] = 0xff800000u;  // -inf: keys past the context length (TMA zero-filled them)
+    mx = fmaxf(mx, __uint_as_float(raw[i]));
+  }
+  const float moff = mx * p.scale_log2;
+  float lsum = 0.f;
+  uint32_t pk[TK / 2];
+#pragma unroll
+  for (int i = 0; i < TK; i += 2) {
+    const float e0 = fast_exp2(__uint_as_float(raw[i]) * p.scale_log2 - moff);
+    const float e1 = fast_exp2(__uint_as_float(raw[i + 1]) * p.scale_log2 - moff);
+    lsum += e0 + e1;
+    pk[i >> 1] = pack_h2(e0, e1);
+  }
+  // P (fp16, two keys per 32-bit column) overwrites the first TK/2 columns of S: every thread owns its lane
+  tmem_st_x32(t_row, pk);
+  tmem_st_x8(t_row + 32, pk + 32);
+  tmem_wait_st();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    constexpr uint32_t idesc_o = umma_idesc_f16(DK, true);
+    tc_fence_after();
+    mbar_wait(bar_v, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int ks = 0; ks < TK / 16; ++ks) {
+      const uint64_t bd = umma_desc_mnmajor_sw128(smem_u32(sV + ks * 2048), TK * 128);
+      umma_f16_ts(tmem_base + Cfg::O_COL, tmem_base + ks * 8, bd, idesc_o, ks != 0 ? 1u : 0u);
+    }
+    umma_commit(bar_o);
+  }
+  mbar_wait(bar_o, 0);
+  tc_fence_after();
+  const int q = q0 + tid;
+  const float inv = 1.f / lsum;
+  __half* orow = p.out + (static_cast<long long>(b) * p.Tq + q) * p.ld_out + head * D;
+#pragma unroll
+  for (int c0 = 0; c0 < D; c0 += 8) {
+    uint32_t o[8];
+    tmem_ld_x8(t_row + Cfg::O_COL + c0, o);
+    tmem_wait_ld();
+    if (q < p.Tq) {
+      *reinterpret_cast<uint4*>(orow + c0) =
+          make_uint4(pack_h2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv),
+                     pack_h2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv),
+                     pack_h2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv),
+                     pack_h2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
 }  // namespace dm

@@ -60,9 +60,12 @@ static int env_or(const char* name, int dflt) {
 }
 static int variant_igemm_pair() { return g_igemm_pair >= 0 ? g_igemm_pair : env_or("DM_IGEMM_PAIR", 1); }
 static int variant_gn_fused() { return g_gn_fused >= 0 ? g_gn_fused : env_or("DM_GN_FUSED", 1); }
+static int g_xattn = -1;
+static int variant_xattn() { return g_xattn >= 0 ? g_xattn : env_or("DM_XATTN", 1); }
 void set_variant(const std::string& name, int value) {
   if (name == "igemm_pair") g_igemm_pair = value;
   else if (name == "gn_fused") g_gn_fused = value;
+  else if (name == "xattn") g_xattn = value;
   else DM_CHECK(false, "unknown kernel variant '" + name + "'");
 }
 
@@ -277,7 +280,9 @@ AttnOp attn_prepare(const AttnDesc& d) {
   // and head_dim 160 stay on the one-tile kernel.  DM_ATTN2=0 disables, DM_ATTN2=2 also routes cross-attention.
   static const int attn2_mode = [] { const char* e = getenv("DM_ATTN2"); return e ? atoi(e) : 1; }();
   op.v2 = (d.D == 40 || d.D == 80) && attn2_mode > 0 && (d.Tk > 128 || attn2_mode > 1) ? 1 : 0;
-  const int bkv = d.D == 40 ? 128 : 64;
+  // short key sets (text cross-attention, <= 80 keys): single-tile kernel with P kept in tensor memory
+  op.xattn = (!op.v2 && d.Tk <= 80 && variant_xattn()) ? 1 : 0;
+  const int bkv = op.xattn ? 80 : d.D == 40 ? 128 : 64;
   auto mk = [&](CUtensorMap* m, const __half* ptr, long long ld, long long bs, int T, int nb, int rows) {
     const uint64_t dims[4] = {static_cast<uint64_t>(d.D), static_cast<uint64_t>(d.heads), static_cast<uint64_t>(T),
                               static_cast<uint64_t>(nb)};
@@ -321,7 +326,27 @@ static void attn2_launch_d(const AttnOp& op, cudaStream_t s) {
   attention2_kernel<D, BKV, ST><<<op.grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
   DM_CUDA(cudaGetLastError());
 }
+template <int D>
+static void xattn_launch_d(const AttnOp& op, cudaStream_t s) {
+  static bool configured = false;
+  using Cfg = XAttnCfg<D>;
+  if (!configured) {
+    DM_CUDA(cudaFuncSetAttribute(xattention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  xattention_kernel<D><<<op.grid, 128, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
+  DM_CUDA(cudaGetLastError());
+}
 void attn_launch(const AttnOp& op, cudaStream_t s) {
+  if (op.xattn) {
+    switch (op.D) {
+      case 40: xattn_launch_d<40>(op, s); break;
+      case 80: xattn_launch_d<80>(op, s); break;
+      case 160: xattn_launch_d<160>(op, s); break;
+      default: DM_CHECK(false, "attention: unsupported head_dim");
+    }
+    return;
+  }
   if (op.v2) {
     if (op.D == 40) attn2_launch_d<40, 128, 2>(op, s);
     else attn2_launch_d<80, 64, 3>(op, s);

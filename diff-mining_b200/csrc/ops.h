@@ -88,7 +88,8 @@ struct AttnOp {
   AttnMaps maps;
   AttnParams p;
   int D = 0;
-  int v2 = 0;  // 1 = warp-specialised two-Q-tile kernel (attention2.cuh)
+  int v2 = 0;     // 1 = warp-specialised two-Q-tile kernel (attention2.cuh)
+  int xattn = 0;  // 1 = short-key-set kernel (<= 80 keys, P in tensor memory)
   dim3 grid;
   double flops = 0;
 };
