@@ -59,8 +59,32 @@ def ops():
         args = (ptr(qkv[..., :C]), ptr(qkv[..., C:2 * C]), ptr(qkv[..., 2 * C:]), 3 * C, 3 * C, 3 * C, T * 3 * C, T * 3 * C, T * 3 * C, B, 8, D, T, T, 0, None, ptr(out), C, stream())
         return lambda: o.check(lib.dm_op_attention(*args)), (qkv, out)
 
+    def xattn(B, T, D):
+        C = 8 * D
+        q = torch.randn(B, T, C, device="cuda").half()
+        kv = torch.randn(2, 77, 2 * C, device="cuda").half()
+        idx = torch.arange(B, device="cuda", dtype=torch.int32) % 2
+        out = torch.empty(B, T, C, device="cuda", dtype=torch.float16)
+        args = (ptr(q), ptr(kv[..., :C]), ptr(kv[..., C:]), C, 2 * C, 2 * C, T * C, 77 * 2 * C, 77 * 2 * C, B, 8, D, T, 77, 2, ptr(idx), ptr(out), C, stream())
+        return lambda: o.check(lib.dm_op_attention(*args)), (q, kv, idx, out)
+
+    def gn(N, HW, C):
+        x = torch.randn(N, HW, C, device="cuda").half()
+        g = torch.randn(C, device="cuda")
+        b = torch.randn(C, device="cuda")
+        out = torch.empty_like(x)
+        return lambda: o.check(lib.dm_op_groupnorm(ptr(x), None, N, HW, C, 0, ptr(g), ptr(b), 1e-5, 1, ptr(out), stream())), (x, g, b, out)
+
+    def ln(rows, C):
+        x = torch.randn(rows, C, device="cuda").half()
+        g = torch.randn(C, device="cuda")
+        b = torch.randn(C, device="cuda")
+        out = torch.empty_like(x)
+        return lambda: o.check(lib.dm_op_layernorm(ptr(x), rows, C, ptr(g), ptr(b), 1e-5, ptr(out), stream())), (x, g, b, out)
+
     targets = [conv(32, 64, 64, 320, 320, 3), conv(32, 64, 64, 320, 2560, 1, geglu=1), conv(32, 64, 64, 320, 320, 1, res=True),
-               conv(32, 16, 16, 1280, 1280, 3), attn(32, 4096, 40), attn(32, 1024, 80)]
+               conv(32, 16, 16, 1280, 1280, 3), conv(32, 32, 32, 1280, 1280, 3), attn(32, 4096, 40), attn(32, 1024, 80),
+               xattn(32, 4096, 40), gn(32, 4096, 320), ln(32 * 4096, 320)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for f, _ in targets:
         for _ in range(2):
