@@ -91,29 +91,6 @@ extern "C" int dm_op_attention(const void* q, const void* k, const void* v, int6
     d.out = static_cast<__half*>(out);
     d.ld_out = ld_out;
     AttnOp op = attn_prepare(d);
-    if (getenv("DM_ATTN_TRACE") && op.v2) {  // debug: clock64 timeline of CTA (0,0,0), printed to stderr
-      const size_t n = 6 * 64 * 8;
-      long long* dev = nullptr;
-      DM_CUDA(cudaMalloc(&dev, n * sizeof(long long)));
-      DM_CUDA(cudaMemset(dev, 0, n * sizeof(long long)));
-      op.p.trace = dev;
-      attn_launch(op, static_cast<cudaStream_t>(stream));
-      DM_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
-      std::vector<long long> h(n);
-      DM_CUDA(cudaMemcpy(h.data(), dev, n * sizeof(long long), cudaMemcpyDeviceToHost));
-      DM_CUDA(cudaFree(dev));
-      long long t0 = 0;
-      for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
-      for (int r = 0; r < 6; ++r)
-        for (int j = 0; j < 64; ++j) {
-          const long long* e = &h[(r * 64 + j) * 8];
-          if (!e[0] && !e[1]) continue;
-          fprintf(stderr, "ATTNTRACE role=%d j=%d", r, j);
-          for (int k = 0; k < 8; ++k) fprintf(stderr, " %lld", e[k] ? e[k] - t0 : -1);
-          fprintf(stderr, "\n");
-        }
-      return;
-    }
     attn_launch(op, static_cast<cudaStream_t>(stream));
   });
 }

@@ -26,7 +26,6 @@ struct AttnParams {
   __half* out;          // [B, Tq, ld_out] ; head h occupies columns [h*D, (h+1)*D)
   long long ld_out;
   float scale_log2;     // d^-0.5 * log2(e)
-  long long* trace;     // debug timeline [6 roles][64 tiles][8 events] of CTA (0,0,0), or null
 };
 
 template <int D, int BKV>

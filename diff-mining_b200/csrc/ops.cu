@@ -297,7 +297,6 @@ AttnOp attn_prepare(const AttnDesc& d) {
   op.p.Tq = d.Tq; op.p.Tk = d.Tk; op.p.B = d.B; op.p.heads = d.heads;
   op.p.kv_index = d.kv_index;
   op.p.out = d.out; op.p.ld_out = d.ld_out;
-  op.p.trace = nullptr;
   op.p.scale_log2 = static_cast<float>(1.0 / std::sqrt(static_cast<double>(d.D)) * 1.4426950408889634);
   op.grid = op.v2 ? dim3((d.Tq + 255) / 256, d.heads, d.B) : dim3((d.Tq + 127) / 128, d.heads, d.B);
   op.flops = 4.0 * d.B * d.heads * static_cast<double>(d.Tq) * d.Tk * d.D;
