@@ -54,7 +54,9 @@ Plan* unet_microbatch(Engine& e, int kind, int aux, const float* x, const int* x
                       const int* noise_index, const long long* t, const int* t_index, const int* ctx_idx, int Bf, int h,
                       int w, cudaStream_t s) {
   Plan* p = e.get_plan(PlanKey{kind, Bf, h, w, aux});
-  patch3x3_launch(x, x_index, noise, noise_index, t, e.sched_a, e.sched_b, Bf, 4, h, w, p->a_in, s);
+  // kPlanUnet with aux = G > 1: the input patch matrix is built once per group of G forwards sharing (x_t, t)
+  const int G = (kind == kPlanUnet && aux > 1) ? aux : 1;
+  patch3x3_launch(x, x_index, noise, noise_index, t, e.sched_a, e.sched_b, Bf / G, 4, h, w, p->a_in, s, G);
   timestep_embed_launch(t, t_index, Bf, p->temb_sin, s);
   DM_CUDA(cudaMemcpyAsync(p->ctx_idx, ctx_idx, Bf * sizeof(int), cudaMemcpyDeviceToDevice, s));
   e.launch_count += 2;
@@ -235,12 +237,15 @@ extern "C" int dm_typicality(dm_engine* h, const float* x0, const float* noise, 
     __half* grid = grid_out ? static_cast<__half*>(grid_out) : ensure_grid(h, static_cast<size_t>(F) * 4 * HW);
     // balanced micro-batches: as few as the cap allows, equal sizes (whole (eps,t) draws: multiples of n_cond), so no
     // small remainder batch under-fills the 148 SMs
-    const long long cap = std::max<long long>(n_cond, max_forwards > 0 ? max_forwards : kDefaultMaxForwards);
+    const long long want = max_forwards > 0 ? max_forwards : kDefaultMaxForwards;
+    const long long cap = std::max<long long>(n_cond, want / n_cond * n_cond);  // whole draws only
     const long long n_mb = (F + cap - 1) / cap;
     const int Bf = static_cast<int>(((F + n_mb - 1) / n_mb + n_cond - 1) / n_cond * n_cond);
     for (long long f0 = 0; f0 < F; f0 += Bf) {
       const int nb = static_cast<int>(std::min<long long>(Bf, F - f0));
-      Plan* p = unet_microbatch(e, kPlanUnet, 0, x0, dev + f0, noise, dev + F + f0, reinterpret_cast<const long long*>(t),
+      // the n_cond forwards of one (eps, t) draw are consecutive rows: share their context-free prefix
+      const int share = (n_cond > 1 && variant_prefix_share()) ? n_cond : 0;
+      Plan* p = unet_microbatch(e, kPlanUnet, share, x0, dev + f0, noise, dev + F + f0, reinterpret_cast<const long long*>(t),
                                 dev + F + f0, dev + 2 * F + f0, nb, hh, ww, s);
       loss_launch(p->out, 16, noise, dev + F + f0, nullptr, nullptr, grid + static_cast<size_t>(f0) * 4 * HW, nullptr, nb, HW,
                   s);

@@ -16,15 +16,16 @@ __global__ void __launch_bounds__(256) patch3x3_kernel(const float* __restrict__
                                                        const int* __restrict__ noise_index,
                                                        const long long* __restrict__ t, const float* __restrict__ ca,
                                                        const float* __restrict__ cb, int Bf, int Cin, int H, int W,
-                                                       __half* __restrict__ out) {
+                                                       int index_stride, __half* __restrict__ out) {
   const long long total = static_cast<long long>(Bf) * H * W * 8;  // 8 x 16-byte vectors per row
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int v = static_cast<int>(idx & 7);
     const long long m = idx >> 3;
     const int x = static_cast<int>(m % W), y = static_cast<int>((m / W) % H), b = static_cast<int>(m / (static_cast<long long>(W) * H));
-    const int xi = x_index ? x_index[b] : b;
-    const int ni = noise_index ? noise_index[b] : b;
+    // index_stride > 1: row b stands for the group of `index_stride` consecutive forwards that share (x_t, t)
+    const int xi = x_index ? x_index[b * index_stride] : b;
+    const int ni = noise_index ? noise_index[b * index_stride] : b;
     float a = 1.f, bb = 0.f;
     if (noise) {
       const long long tt = t[ni];
@@ -62,6 +63,19 @@ __global__ void timestep_embed_kernel(const long long* __restrict__ t, const int
   const float e = tt * f;
   out[b * 320 + k] = __float2half_rn(cosf(e));
   out[b * 320 + 160 + k] = __float2half_rn(sinf(e));
+}
+
+// out[(u*G + g), :] = in[u, :], g < G: replicates the activations computed once per (x_t, t) group to every
+// condition row of the group (cond/uncond prefix sharing); `row_vecs` = 16-byte vectors per row
+__global__ void __launch_bounds__(256) repeat_rows_kernel(const uint4* __restrict__ in, long long rows, long long row_vecs,
+                                                          int G, uint4* __restrict__ out) {
+  const long long total = rows * row_vecs;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long u = idx / row_vecs, v = idx % row_vecs;
+    const uint4 val = __ldg(in + idx);
+    for (int g = 0; g < G; ++g) out[(u * G + g) * row_vecs + v] = val;
+  }
 }
 
 // nearest resize NHWC -> NHWC (torch 'nearest': src = min(floor(dst * in/out), in-1))

@@ -304,14 +304,14 @@ __global__ void __launch_bounds__(384) gn_fused_kernel(NormSrc s0, NormSrc s1, i
     *reinterpret_cast<uint4*>(obase + static_cast<long long>(px) * C) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   };
   int px = p0 + r;
-  for (; px + 3 * R < p1; px += 4 * R) {
-    const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(base + px * ps));
-    const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(base + (px + R) * ps));
-    const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(base + (px + 2 * R) * ps));
-    const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(base + (px + 3 * R) * ps));
-    apply(u0, px); apply(u1, px + R); apply(u2, px + 2 * R); apply(u3, px + 3 * R);
+  for (; px + 7 * R < p1; px += 8 * R) {
+    uint4 u[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) u[k] = __ldcg(reinterpret_cast<const uint4*>(base + (px + k * R) * ps));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) apply(u[k], px + k * R);
   }
-  for (; px < p1; px += R) apply(__ldg(reinterpret_cast<const uint4*>(base + px * ps)), px);
+  for (; px < p1; px += R) apply(__ldcg(reinterpret_cast<const uint4*>(base + px * ps)), px);
 }
 
 // LayerNorm over the last dim (C <= 32*8*MAXV, multiple of 8).  Persistent warps: a warp walks rows

@@ -60,12 +60,14 @@ static int env_or(const char* name, int dflt) {
 }
 static int variant_igemm_pair() { return g_igemm_pair >= 0 ? g_igemm_pair : env_or("DM_IGEMM_PAIR", 1); }
 static int variant_gn_fused() { return g_gn_fused >= 0 ? g_gn_fused : env_or("DM_GN_FUSED", 1); }
-static int g_xattn = -1;
+static int g_xattn = -1, g_prefix = -1;
+int variant_prefix_share() { return g_prefix >= 0 ? g_prefix : env_or("DM_PREFIX_SHARE", 1); }
 static int variant_xattn() { return g_xattn >= 0 ? g_xattn : env_or("DM_XATTN", 1); }
 void set_variant(const std::string& name, int value) {
   if (name == "igemm_pair") g_igemm_pair = value;
   else if (name == "gn_fused") g_gn_fused = value;
   else if (name == "xattn") g_xattn = value;
+  else if (name == "prefix_share") g_prefix = value;
   else DM_CHECK(false, "unknown kernel variant '" + name + "'");
 }
 
@@ -404,7 +406,15 @@ void gn_launch(const GnDesc& d, cudaStream_t s) {
   const size_t smem = static_cast<size_t>(g.VT) * g.R * 8 * 2 * sizeof(float);
   // images that fit in L2 comfortably: one fused kernel, one cluster per image (1 HBM read + 1 write)
   if (gn_use_fused(d.HW, C)) {
-    const int CL = d.HW >= 512 ? 8 : d.HW >= 256 ? 4 : d.HW >= 128 ? 2 : 1;  // depends on HW only (batch invariance)
+    // cluster size depends on HW only (batch invariance); 16 = non-portable size, allowed on sm_100
+    static const int cl_max = env_or("DM_GN_CLUSTER", 8);  // 16 measured 8 % slower (r01)
+    int CL = d.HW >= 2048 ? 16 : d.HW >= 512 ? 8 : d.HW >= 256 ? 4 : d.HW >= 128 ? 2 : 1;
+    CL = std::min(CL, cl_max);
+    static bool configured = false;
+    if (!configured) {
+      DM_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      configured = true;
+    }
     const int px_per = (d.HW + CL - 1) / CL;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(CL, d.Nimg, 1);
@@ -445,10 +455,17 @@ void layernorm_launch(const __half* x, long long ld_x, const float* gamma, const
 }
 
 void patch3x3_launch(const float* x0, const int* x_index, const float* noise, const int* noise_index, const long long* t,
-                     const float* ca, const float* cb, int Bf, int Cin, int H, int W, __half* out, cudaStream_t s) {
+                     const float* ca, const float* cb, int Bf, int Cin, int H, int W, __half* out, cudaStream_t s,
+                     int index_stride) {
   DM_CHECK(9 * Cin <= 64, "patch3x3: Cin too large");
   patch3x3_kernel<<<grid_for(static_cast<long long>(Bf) * H * W * 8), 256, 0, s>>>(x0, x_index, noise, noise_index, t, ca,
-                                                                                   cb, Bf, Cin, H, W, out);
+                                                                                   cb, Bf, Cin, H, W, index_stride, out);
+  DM_CUDA(cudaGetLastError());
+}
+void repeat_rows_launch(const __half* in, long long rows, long long row_elems, int G, __half* out, cudaStream_t s) {
+  DM_CHECK(row_elems % 8 == 0 && G >= 1, "repeat_rows: row length must be a multiple of 8");
+  repeat_rows_kernel<<<grid_for(rows * (row_elems / 8)), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), rows, row_elems / 8, G,
+                                                                     reinterpret_cast<uint4*>(out));
   DM_CUDA(cudaGetLastError());
 }
 void timestep_embed_launch(const long long* t, const int* t_index, int Bf, __half* out, cudaStream_t s) {

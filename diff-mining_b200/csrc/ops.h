@@ -115,7 +115,10 @@ void gn_launch(const GnDesc& d, cudaStream_t s);
 void layernorm_launch(const __half* x, long long ld_x, const float* gamma, const float* beta, float eps, long long rows,
                       int C, __half* out, long long ld_out, cudaStream_t s);
 void patch3x3_launch(const float* x0, const int* x_index, const float* noise, const int* noise_index, const long long* t,
-                     const float* ca, const float* cb, int Bf, int Cin, int H, int W, __half* out, cudaStream_t s);
+                     const float* ca, const float* cb, int Bf, int Cin, int H, int W, __half* out, cudaStream_t s,
+                     int index_stride = 1);
+void repeat_rows_launch(const __half* in, long long rows, long long row_elems, int G, __half* out, cudaStream_t s);
+int variant_prefix_share();  // 1 = run the (x_t, t)-only prefix of the U-Net once per draw in dm_typicality
 void timestep_embed_launch(const long long* t, const int* t_index, int Bf, __half* out, cudaStream_t s);
 void upsample_nearest_launch(const __half* in, int N, int H, int W, int C, int Ho, int Wo, __half* out, cudaStream_t s);
 void space_to_planes_launch(const __half* in, int N, int H, int W, int C, int H2, int W2, __half* out, cudaStream_t s);

@@ -11,6 +11,7 @@ namespace {
 struct UnetBuilder : Builder {
   int Bf = 0;
   __half* tproj = nullptr;  // [Bf, tproj_total] stacked time_emb_proj outputs
+  int tproj_row_mult = 1;   // > 1 while building the shared prefix: row u of the activations <-> row u*G of tproj
   using Builder::Builder;
 
   // ResnetBlock2D (reference op order: applications/parallel-dataset/pnp.py:282-359)
@@ -18,7 +19,7 @@ struct UnetBuilder : Builder {
     const int Cin = x0.C + (x1 ? x1->C : 0);
     Act n1 = groupnorm(key + ".norm1", x0, x1, key + ".norm1", 1e-5f, true);
     const __half* rb = dry ? nullptr : tproj + e.tproj_off.at(key);
-    Act h1 = conv3x3(key + ".conv1", n1, nullptr, key + ".conv1", Cout, rb, e.tproj_total, nullptr);
+    Act h1 = conv3x3(key + ".conv1", n1, nullptr, key + ".conv1", Cout, rb, e.tproj_total * tproj_row_mult, nullptr);
     release(n1);
     Act n2 = groupnorm(key + ".norm2", h1, nullptr, key + ".norm2", 1e-5f, true);
     release(h1);
@@ -35,8 +36,9 @@ struct UnetBuilder : Builder {
     return out;
   }
 
-  // Transformer2DModel with one BasicTransformerBlock (self-attn, cross-attn, GEGLU FF)
-  Act transformer(const std::string& key, const Act& x) {
+  // Transformer2DModel with one BasicTransformerBlock (self-attn, cross-attn, GEGLU FF), in two halves: everything up
+  // to and including the self-attention residual depends on (x_t, t) only; the context enters in the tail.
+  Act transformer_head(const std::string& key, const Act& x) {
     const int C = x.C, D = C / 8, T = x.H * x.W;
     const std::string t = key + ".transformer_blocks.0";
     Act n = groupnorm(key + ".norm", x, nullptr, key + ".norm", 1e-6f, false);
@@ -60,6 +62,13 @@ struct UnetBuilder : Builder {
     Act h2 = linear(t + ".attn1.to_out.0", ao, nullptr, t + ".attn1.to_out.0", C, true, &h);
     release(ao);
     release(h);
+    return h2;
+  }
+
+  // consumes h2 (released); x is the block input (residual of proj_out)
+  Act transformer_tail(const std::string& key, const Act& x, Act& h2) {
+    const int C = x.C, D = C / 8, T = x.H * x.W;
+    const std::string t = key + ".transformer_blocks.0";
     // --- cross attention against the cached per-slot K/V
     Act ln2 = layernorm(t + ".norm2", h2, t + ".norm2");
     Act q2 = linear(t + ".attn2.to_q", ln2, nullptr, t + ".attn2.to_q", C, false, nullptr);
@@ -93,6 +102,23 @@ struct UnetBuilder : Builder {
     release(h4);
     tap(key, out);
     return out;
+  }
+
+  Act transformer(const std::string& key, const Act& x) {
+    Act h2 = transformer_head(key, x);
+    return transformer_tail(key, x, h2);
+  }
+
+  // replicate every row of x (N = groups) G times -> N*G rows (cond/uncond prefix sharing)
+  Act repeat_rows(const std::string& name, const Act& x, int G) {
+    Act o = alloc(x.N * G, x.H, x.W, x.C);
+    if (!dry) {
+      const __half* in = hp(x);
+      __half* out = hp(o);
+      const long long rows = x.N, elems = static_cast<long long>(x.H) * x.W * x.C;
+      push(Step{[=](cudaStream_t s) { repeat_rows_launch(in, rows, elems, G, out, s); }, kStepOther, 0, 1, name});
+    }
+    return o;
   }
 
   Act downsample(const std::string& key, const Act& x) {
@@ -145,12 +171,19 @@ void build_unet_plan(Engine& e, Plan& p, bool dry, ArenaPlanner& ar) {
   UnetBuilder b(e, p, dry, ar);
   const int Bf = p.key.B, h = p.key.h, w = p.key.w;
   const int up_ft = p.key.kind == kPlanDift ? p.key.aux : -1;
+  // kPlanUnet with aux = G > 1: rows come in groups of G consecutive forwards that share (x_t, t) and differ only in
+  // the context (dm_typicality: cond fastest).  Everything before the first cross-attention -- conv_in,
+  // down_blocks.0.resnets.0 and the first transformer up to its self-attention residual -- is computed once per
+  // group on Bu = Bf / G rows and replicated; results are bit-identical to the unshared plan.
+  const int G = (p.key.kind == kPlanUnet && p.key.aux > 1) ? p.key.aux : 1;
+  DM_CHECK(Bf % G == 0, "shared-prefix plan: batch is not a multiple of the group size");
+  const int Bu = Bf / G;
   b.Bf = Bf;
   const std::string U = "unet.";
   static const int ch[4] = {320, 640, 1280, 1280};
 
   // ---- boundary buffers
-  const size_t off_ain = b.alloc_bytes(static_cast<size_t>(Bf) * h * w * 64 * sizeof(__half));
+  const size_t off_ain = b.alloc_bytes(static_cast<size_t>(Bu) * h * w * 64 * sizeof(__half));
   const size_t off_sin = b.alloc_bytes(static_cast<size_t>(Bf) * 320 * sizeof(__half));
   const size_t off_ctx = b.alloc_bytes(static_cast<size_t>(Bf) * sizeof(int));
   p.a_in = b.at<__half>(off_ain);
@@ -167,19 +200,38 @@ void build_unet_plan(Engine& e, Plan& p, bool dry, ArenaPlanner& ar) {
   b.tproj = b.hp(tp);
 
   // ---- conv_in as a K=64 GEMM over the 36-wide 3x3x4 patch matrix
-  Act ain; ain.off = off_ain; ain.N = Bf; ain.H = h; ain.W = w; ain.C = 64; ain.valid = true;
+  Act ain; ain.off = off_ain; ain.N = Bu; ain.H = h; ain.W = w; ain.C = 64; ain.valid = true;
   Act x = b.linear("conv_in", ain, nullptr, U + "conv_in", 320, true, nullptr);
   b.tap("conv_in", x);
 
   std::vector<Act> skips;
-  skips.push_back(x);
+  if (G == 1) skips.push_back(x);
   // ---- down path
   for (int i = 0; i < 4; ++i) {
     for (int j = 0; j < 2; ++j) {
       const std::string rk = U + "down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j);
+      const std::string ak = U + "down_blocks." + std::to_string(i) + ".attentions." + std::to_string(j);
+      if (G > 1 && i == 0 && j == 0) {
+        // shared prefix on Bu rows, then fan out to the Bf condition rows
+        b.tproj_row_mult = G;
+        Act r_u = b.resnet(rk, x, nullptr, ch[i]);
+        b.tproj_row_mult = 1;
+        Act h2_u = b.transformer_head(ak, r_u);
+        Act s0 = b.repeat_rows("conv_in.fanout", x, G);
+        b.release(x);
+        skips.push_back(s0);
+        Act r_f = b.repeat_rows(rk + ".fanout", r_u, G);
+        b.release(r_u);
+        Act h2_f = b.repeat_rows(ak + ".attn1.fanout", h2_u, G);
+        b.release(h2_u);
+        Act a = b.transformer_tail(ak, r_f, h2_f);
+        b.release(r_f);
+        x = a;
+        skips.push_back(x);
+        continue;
+      }
       Act r = b.resnet(rk, x, nullptr, ch[i]);
       if (i < 3) {
-        const std::string ak = U + "down_blocks." + std::to_string(i) + ".attentions." + std::to_string(j);
         Act a = b.transformer(ak, r);
         b.release(r);
         r = a;

@@ -53,6 +53,11 @@ class Engine:
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def set_variant(self, name: str, value: int) -> None:
+        """kernel-variant switch for tests / A-B timing (process-wide; -1 = default): "igemm_pair", "gn_fused", "xattn",
+        "prefix_share" (include/dm_abi.h: dm_op_set_variant).  Plans built earlier keep the variant they were built with."""
+        _abi.check(self.lib.dm_op_set_variant(name.encode(), int(value)))
+
     # ---------------------------------------------------------------- weights / context / schedule
     def load_state_dict(self, sd: Dict[str, torch.Tensor], prefix: str) -> None:
         """prefix is 'unet.' or 'vae.' ; keys follow the diffusers schema."""

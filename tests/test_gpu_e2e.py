@@ -133,6 +133,24 @@ def test_typicality_grid_and_T(engine, unet_weights_gpu, contexts):
     assert torch.equal(grid, grid2) and torch.equal(T, T2)
 
 
+def test_typicality_prefix_sharing_is_bit_identical(engine):
+    """dm_typicality runs the context-free prefix of the U-Net (conv_in, down_blocks.0.resnets.0, the first
+    self-attention) once per (eps, t) draw and fans it out to the n_cond condition rows: not one bit may change"""
+    Bi, N, h, w = 2, 3, 32, 32
+    g = torch.Generator().manual_seed(21)
+    x0 = torch.randn(Bi, 4, h, w, generator=g)
+    noise = torch.randn(N, 4, h, w, generator=g)
+    t = torch.randint(100, 700, (N,), generator=g)
+    out = {}
+    for share in (1, 0):
+        engine.set_variant("prefix_share", share)
+        for slots in ([1, 0], [1, 2, 0]):
+            out[(share, len(slots))] = engine.typicality(x0, noise, t, slots, max_forwards=6 if share else 12)
+    engine.set_variant("prefix_share", -1)
+    for n_cond in (2, 3):
+        assert torch.equal(out[(1, n_cond)][0], out[(0, n_cond)][0]) and torch.equal(out[(1, n_cond)][1], out[(0, n_cond)][1])
+
+
 def test_typicality_properties_full_size(engine):
     """BASELINE config-2 latent size (64x64): size-independent properties instead of an oracle run"""
     Bi, N, h, w = 2, 4, 64, 64
