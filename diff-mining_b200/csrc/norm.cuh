@@ -315,30 +315,50 @@ __global__ void __launch_bounds__(384) gn_fused_kernel(NormSrc s0, NormSrc s1, i
 }
 
 // LayerNorm over the last dim (C <= 32*8*MAXV, multiple of 8).  Persistent warps: a warp walks rows
-// w, w+W, ... holding one row in registers while the next row's loads are already in flight; gamma / beta
-// live in registers as packed halves (they are fp16 values).
+// w, w+W, ... holding one row in registers while the next row's loads are already in flight.  The kernel is
+// FMA-pipe-bound, not HBM-bound (plain fp32 FMA-pipe instructions issue every other cycle), so all per-element math
+// runs on packed f32x2 instructions and gamma / beta are read as float pairs from shared memory (LSU pipe).
+__device__ __forceinline__ uint64_t ln_pack(float a, float b) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ void ln_unpack(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ln_fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t ln_add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t ln_mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, long long ld_x,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, long long rows,
                                                         int C, __half* __restrict__ out, long long ld_out) {
+  extern __shared__ float sm_ln[];  // gamma[C] | beta[C]
+  float* sg = sm_ln;
+  float* sb = sm_ln + C;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    sg[i] = gamma[i];
+    sb[i] = beta[i];
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long nw = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
   long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int vcols = C >> 3;
-  uint32_t gp[MAXV][4], bp[MAXV][4];
-#pragma unroll
-  for (int k = 0; k < MAXV; ++k) {
-    const int vc = lane + 32 * k;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      gp[k][i] = 0; bp[k][i] = 0;
-      if (vc < vcols) {
-        gp[k][i] = pack_h2(gamma[(vc << 3) + 2 * i], gamma[(vc << 3) + 2 * i + 1]);
-        bp[k][i] = pack_h2(beta[(vc << 3) + 2 * i], beta[(vc << 3) + 2 * i + 1]);
-      }
-    }
-  }
   uint4 cur[MAXV], nxt[MAXV];
   auto load = [&](uint4* dst, long long rw) {
 #pragma unroll
@@ -353,42 +373,58 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
   while (row < rows) {
     const long long nrow = row + nw;
     if (nrow < rows) load(nxt, nrow);
-    float v[MAXV][8];
-    float s = 0.f;
+    uint64_t v[MAXV][4];  // the row slice as packed fp32 pairs
+    uint64_t s2 = ln_pack(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
       const __half2* h = reinterpret_cast<const __half2*>(&cur[k]);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 f = __half22float2(h[i]);
-        v[k][2 * i] = f.x; v[k][2 * i + 1] = f.y;
-        s += f.x + f.y;  // lanes past vcols hold zeros
+        v[k][i] = ln_pack(f.x, f.y);
+        s2 = ln_add2(s2, v[k][i]);  // lanes past vcols hold zeros
       }
     }
+    float sa, sb2;
+    ln_unpack(s2, sa, sb2);
+    float s = sa + sb2;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s * invC;
-    float q = 0.f;
+    const uint64_t nm2 = ln_pack(-mean, -mean);
+    uint64_t q2 = ln_pack(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
       if (lane + 32 * k < vcols) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { const float d = v[k][i] - mean; q += d * d; }
+        for (int i = 0; i < 4; ++i) {
+          v[k][i] = ln_add2(v[k][i], nm2);  // d = x - mean
+          q2 = ln_fma2(v[k][i], v[k][i], q2);
+        }
       }
     }
+    float qa, qb;
+    ln_unpack(q2, qa, qb);
+    float q = qa + qb;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q * invC + eps);
+    const uint64_t r2 = ln_pack(rstd, rstd);
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
       const int vc = lane + 32 * k;
       if (vc < vcols) {
+        const float4* g4 = reinterpret_cast<const float4*>(sg + (vc << 3));
+        const float4* b4 = reinterpret_cast<const float4*>(sb + (vc << 3));
         uint32_t pk[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 g = __half22float2(*reinterpret_cast<const __half2*>(&gp[k][i]));
-          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&bp[k][i]));
-          pk[i] = pack_h2((v[k][2 * i] - mean) * rstd * g.x + b.x, (v[k][2 * i + 1] - mean) * rstd * g.y + b.y);
+        for (int i = 0; i < 2; ++i) {
+          const float4 g = g4[i], b = b4[i];
+          float y0, y1, y2, y3;
+          ln_unpack(ln_fma2(ln_mul2(v[k][2 * i], r2), ln_pack(g.x, g.y), ln_pack(b.x, b.y)), y0, y1);
+          ln_unpack(ln_fma2(ln_mul2(v[k][2 * i + 1], r2), ln_pack(g.z, g.w), ln_pack(b.z, b.w)), y2, y3);
+          pk[2 * i] = pack_h2(y0, y1);
+          pk[2 * i + 1] = pack_h2(y2, y3);
         }
         *reinterpret_cast<uint4*>(out + row * ld_out + (vc << 3)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }

@@ -444,13 +444,23 @@ void gn_launch(const GnDesc& d, cudaStream_t s) {
 void layernorm_launch(const __half* x, long long ld_x, const float* gamma, const float* beta, float eps, long long rows,
                       int C, __half* out, long long ld_out, cudaStream_t s) {
   DM_CHECK(C % 8 == 0 && C <= 1280, "layernorm: C must be a multiple of 8 and <= 1280");
-  // persistent warps: 8 per block, enough blocks to fill the machine (148 SMs x 8 resident blocks)
+  // persistent warps: 8 per block, exactly as many blocks as are co-resident (a second wave would start late and
+  // leave the tail of the row range to half the machine)
   const long long want = (rows + 7) / 8;
-  const unsigned blocks = static_cast<unsigned>(std::max<long long>(1, std::min<long long>(want, 148 * 8)));
   const int maxv = (C / 8 + 31) / 32;
-  if (maxv <= 2) layernorm_kernel<2><<<blocks, 256, 0, s>>>(x, ld_x, gamma, beta, eps, rows, C, out, ld_out);
-  else if (maxv == 3) layernorm_kernel<3><<<blocks, 256, 0, s>>>(x, ld_x, gamma, beta, eps, rows, C, out, ld_out);
-  else layernorm_kernel<5><<<blocks, 256, 0, s>>>(x, ld_x, gamma, beta, eps, rows, C, out, ld_out);
+  const size_t smem = 2 * static_cast<size_t>(C) * sizeof(float);
+  auto launch = [&](auto kernel, int& occ_cache) {
+    if (occ_cache == 0) {
+      DM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, kernel, 256, smem));
+      occ_cache = std::max(1, occ_cache);
+    }
+    const unsigned blocks = static_cast<unsigned>(std::max<long long>(1, std::min<long long>(want, 148ll * occ_cache)));
+    kernel<<<blocks, 256, smem, s>>>(x, ld_x, gamma, beta, eps, rows, C, out, ld_out);
+  };
+  static int occ2 = 0, occ3 = 0, occ5 = 0;
+  if (maxv <= 2) launch(layernorm_kernel<2>, occ2);
+  else if (maxv == 3) launch(layernorm_kernel<3>, occ3);
+  else launch(layernorm_kernel<5>, occ5);
   DM_CUDA(cudaGetLastError());
 }
 
