@@ -16,12 +16,16 @@
 //
 // A softmax thread pulls its half S row into registers in one TMEM pass and releases S at once (s_free), so
 // QK^T of tile j+1 is issued while the exponentials of tile j are still being computed; P is double-buffered in
-// shared memory so P_q V_j runs under the softmax of tile j+1 without a wait; the two warpgroups are started half
-// a tile apart so that one of them always feeds the MUFU pipe.  Row max via 3-input FMNMX, scale/offset and row sums via packed f32x2 FMA/ADD.
+// shared memory so P_q V_j runs under the softmax of tile j+1 without a wait; the two groups hand an "XU token"
+// (named barriers 4 / 5) back and forth so that their exponential phases alternate instead of colliding.  Row max via 3-input FMNMX, scale/offset and row sums via packed f32x2 FMA/ADD.
 // O is rescaled in TMEM only when the row max grew by more than 2^8 (lazy rescale: P stays <= 256 in fp16, the
 // final O / l is unchanged up to fp32 rounding).
 #pragma once
 #include "attention.cuh"
+
+#ifndef DM_ATTN_PINGPONG
+#define DM_ATTN_PINGPONG 1
+#endif
 
 namespace dm {
 
@@ -225,6 +229,9 @@ __global__ void __launch_bounds__(640, 1) attention2_kernel(const __grid_constan
     const uint64_t sc2 = pack_f2(sc, sc);
     float m_ref = -INFINITY;
     uint64_t l2 = pack_f2(0.f, 0.f);
+#if DM_ATTN_PINGPONG
+    if (wg == 1) asm volatile("bar.arrive 4, 512;" ::: "memory");  // group 0 exponentiates first
+#endif
     // O columns (in 16-column TMEM chunks) this thread rescales on the rare path
     constexpr int NCH16 = DK / 16;
     const int ch_lo = half == 0 ? 0 : (NCH16 + 1) / 2, ch_hi = half == 0 ? (NCH16 + 1) / 2 : NCH16;
@@ -276,13 +283,18 @@ __global__ void __launch_bounds__(640, 1) attention2_kernel(const __grid_constan
       }
       // P buffer j&1 was last read by PV(j-2)
       if (j >= 2) mbar_wait(&o_full_q[jp], ((j - 2) >> 1) & 1);
-      if (j == 0 && wg == 1) asm volatile("bar.sync 1, 512;" ::: "memory");  // start half a tile behind group 0
       {
         float la, lb;
         unpack_f2(l2, la, lb);
         l2 = pack_f2(la * alpha, lb * alpha);
       }
       m_ref = m_new;
+#if DM_ATTN_PINGPONG
+      // ping-pong: the MUFU-bound exponential phases of the two groups alternate, so one group's TMEM reads, row
+      // maxima and barrier waits run under the other group's exponentials (token = named barrier 4 + group)
+      if (wg == 0) asm volatile("bar.sync 4, 512;" ::: "memory");
+      else asm volatile("bar.sync 5, 512;" ::: "memory");
+#endif
       const float nmoff = -m_ref * sc;
       const uint64_t off2 = pack_f2(nmoff, nmoff);
       uint8_t* sPb = sPq + jp * Cfg::P_TILE_BYTES;
@@ -303,8 +315,12 @@ __global__ void __launch_bounds__(640, 1) attention2_kernel(const __grid_constan
         const int c = half * HC + c0;  // column inside the BKV-wide P tile
         const uint32_t off = (c >> 6) * 16384 + ((((c & 63) >> 3) ^ (row & 7)) << 4);
         *reinterpret_cast<uint4*>(sPb + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        if (c0 == HC / 2 - 8 && j == 0 && wg == 0) asm volatile("bar.arrive 1, 512;" ::: "memory");
       }
+#if DM_ATTN_PINGPONG
+      // hand the XU token to the other group (group 1 keeps its last one: group 0 has no tile left to wait for)
+      if (wg == 0) asm volatile("bar.arrive 5, 512;" ::: "memory");
+      else if (j + 1 < nkv) asm volatile("bar.arrive 4, 512;" ::: "memory");
+#endif
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
