@@ -87,52 +87,19 @@ struct IgCfg {
 
 // Phi(x) * x with erfc from Abramowitz-Stegun 7.1.26 (|abs err| < 4.3e-7 on the result: within one fp16 ulp of
 // the erf formulation everywhere, closer to the exact value than 0.5*x*(1+erff(x/sqrt2)) on the negative tail).
-// Branch-free and evaluated for TWO arguments at once on packed f32x2 FMA-pipe instructions (the plain fp32 FMA
-// pipe issues one warp instruction every two cycles, so the GEGLU epilogue is FMA-pipe-bound, not MUFU-bound):
-// 12 packed FMA-pipe ops + 4 MUFU + 4 ALU ops per pair.
-__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
-  uint64_t d;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(a), "f"(b));
-  return d;
-}
-__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint64_t f2_bcast(float a) { return f2_pack(a, a); }
-
-__device__ __forceinline__ void gelu_fast2(float x0, float x1, float& y0, float& y1) {
-  const uint64_t x = f2_pack(x0, x1);
-  const uint64_t z = f2_mul(f2_pack(fabsf(x0), fabsf(x1)), f2_bcast(0.70710678118654752f));
-  float d0, d1;
-  f2_unpack(f2_fma(z, f2_bcast(0.3275911f), f2_bcast(1.f)), d0, d1);
-  const uint64_t t = f2_pack(fast_rcp(d0), fast_rcp(d1));
-  uint64_t pl = f2_fma(t, f2_bcast(0.5f * 1.061405429f), f2_bcast(0.5f * -1.453152027f));
-  pl = f2_fma(t, pl, f2_bcast(0.5f * 1.421413741f));
-  pl = f2_fma(t, pl, f2_bcast(0.5f * -0.284496736f));
-  pl = f2_fma(t, pl, f2_bcast(0.5f * 0.254829592f));
-  float w0, w1;
-  f2_unpack(f2_mul(f2_mul(z, f2_bcast(-1.4426950408889634f)), z), w0, w1);
-  const uint64_t q = f2_mul(f2_mul(pl, t), f2_pack(fast_exp2(w0), fast_exp2(w1)));  // 0.5 * erfc(|x| / sqrt 2)
-  const uint64_t omq = f2_fma(q, f2_bcast(-1.f), f2_bcast(1.f));
-  float q0, q1, o0, o1;
-  f2_unpack(q, q0, q1);
-  f2_unpack(omq, o0, o1);
-  f2_unpack(f2_mul(x, f2_pack(x0 < 0.f ? q0 : o0, x1 < 0.f ? q1 : o1)), y0, y1);
+// Branch-free: 12 scalar FMA-pipe ops + 2 MUFU + 2 ALU ops.  (Scalar on purpose: on B200 a packed f32x2 FMA issues
+// every 3.1 cycles per sub-partition against 1.08 for a scalar FFMA -- tools/microbench/fma.cu -- and the GEGLU
+// epilogue is FMA-pipe-bound.)
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.f));
+  float pl = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  pl = fmaf(t, pl, 0.5f * 1.421413741f);
+  pl = fmaf(t, pl, 0.5f * -0.284496736f);
+  pl = fmaf(t, pl, 0.5f * 0.254829592f);
+  const float e = fast_exp2((x * -0.72134752044448170f) * x);  // exp(-x^2 / 2)
+  const float q = (pl * t) * e;                                 // 0.5 * erfc(|x| / sqrt 2)
+  return x * (x < 0.f ? q : 1.f - q);
 }
 
 __device__ __forceinline__ __half2 u2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
@@ -475,9 +442,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
               const __half2 val = __floats2half2_rn(__uint_as_float(raw[4 * i]) + bb.x, __uint_as_float(raw[4 * i + 2]) + bb.z);
               const __half2 gate = __floats2half2_rn(__uint_as_float(raw[4 * i + 1]) + bb.y, __uint_as_float(raw[4 * i + 3]) + bb.w);
               const float2 gf = __half22float2(gate);
-              float a0, a1;
-              gelu_fast2(gf.x, gf.y, a0, a1);
-              const __half2 act = __floats2half2_rn(a0, a1);
+              const __half2 act = __floats2half2_rn(gelu_fast(gf.x), gelu_fast(gf.y));
               pk[i] = h2u(__hmul2(val, act));
             }
           } else {
