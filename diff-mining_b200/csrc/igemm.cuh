@@ -31,7 +31,7 @@ constexpr int IG_BM = 128;
 constexpr int IG_BK = 64;
 constexpr int IG_CW = 32;                           // output columns per epilogue chunk
 constexpr int IG_CHUNK_BYTES = IG_BM * IG_CW * 2;   // 8 KB
-constexpr int IG_THREADS = 64 + 256;
+constexpr int IG_THREADS = 64 + 256;   // default: two epilogue warpgroups (NG = 2)
 
 struct IgSeg {
   int16_t src, dy, dx, pad_;
@@ -66,23 +66,26 @@ struct IgParams {
 // CG = CTAs per tile: 1, or 2 = a CTA pair (cta_group::2) computing a 256 x BN tile with each CTA holding its 128
 // rows of A and HALF of the B tile, which cuts the per-SM shared-memory operand traffic and the L2 -> SM weight
 // traffic by the B half.
-template <int BN, bool DIRECT, int CG = 1>
+// NG = epilogue warpgroups (2, or 4 for the short-K layers whose epilogue, not the MMA, bounds the tile time).
+template <int BN, bool DIRECT, int CG = 1, int NG = 2>
 struct IgCfg {
+  static constexpr int THREADS = 64 + 128 * NG;
   static constexpr int A_BYTES = IG_BM * IG_BK * 2;
   static constexpr int B_BYTES = (BN / CG) * IG_BK * 2;
   static_assert(CG == 1 || (CG == 2 && !DIRECT && BN % 32 == 0), "CTA pairs: staged epilogue, BN multiple of 32");
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int NBG = DIRECT ? 0 : (BN >= 256 ? 2 : 4);  // chunk buffers per epilogue warpgroup
+  static constexpr int NBG = DIRECT ? 0 : (BN >= 256 || NG > 2) ? 2 : 4;  // chunk buffers per epilogue warpgroup
   static constexpr int LOOKAHEAD = NBG >= 4 ? 2 : 1;             // residual prefetch distance (chunks)
-  static constexpr int RING_BYTES = 2 * NBG * IG_CHUNK_BYTES;
-  static constexpr int BIAS_BYTES = 2 * BN * 4;
+  static constexpr int RING_BYTES = NG * NBG * IG_CHUNK_BYTES;
+  static constexpr int BIAS_BYTES = NG * BN * 4;
   static constexpr int BAR_BYTES = 256;
   static constexpr int RAW_STAGES = (232448 - RING_BYTES - BIAS_BYTES - BAR_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RING_BYTES + BIAS_BYTES + BAR_BYTES;
   static_assert(STAGES >= 3, "pipeline too shallow");
-  static_assert(2 * STAGES + 4 + 4 * 2 + 1 <= BAR_BYTES / 8, "barrier area");
+  static_assert(2 * STAGES + 4 + NG * (NBG > 0 ? NBG : 1) + 1 <= BAR_BYTES / 8, "barrier area");
+  static_assert(NG == 2 || (NG == 4 && !DIRECT && CG == 1), "four epilogue groups: staged epilogue, single CTA");
 };
 
 // Phi(x) * x with erfc from Abramowitz-Stegun 7.1.26 (|abs err| < 4.3e-7 on the result: within one fp16 ulp of
@@ -109,9 +112,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int BN, bool DIRECT, int CG>
-__global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_constant__ IgMaps maps, const IgParams p) {
-  using Cfg = IgCfg<BN, DIRECT, CG>;
+template <int BN, bool DIRECT, int CG, int NG>
+__global__ void __launch_bounds__(64 + 128 * NG, 1) igemm_kernel(const __grid_constant__ IgMaps maps, const IgParams p) {
+  using Cfg = IgCfg<BN, DIRECT, CG, NG>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NBG = Cfg::NBG;
   extern __shared__ __align__(1024) uint8_t smem[];  // 128B-swizzled tiles need 1024-byte alignment
@@ -125,8 +128,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
-  uint64_t* rfull = bars + 2 * STAGES + 4;  // [2 groups][NBG]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 8);
+  uint64_t* rfull = bars + 2 * STAGES + 4;  // [NG groups][NBG]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + NG * (NBG > 0 ? NBG : 1));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -141,9 +144,9 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
     }
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 8 * CG);  // CG == 2: the leader's collects the epilogue warps of both CTAs
-    mbar_init(&tempty[1], 8 * CG);
-    for (int i = 0; i < 8; ++i) mbar_init(&rfull[i], 1);
+    mbar_init(&tempty[0], 4 * NG * CG);  // CG == 2: the leader's collects the epilogue warps of both CTAs
+    mbar_init(&tempty[1], 4 * NG * CG);
+    for (int i = 0; i < NG * (NBG > 0 ? NBG : 1); ++i) mbar_init(&rfull[i], 1);
     fence_barrier_init();
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.b);
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
-        for (int c0 = eg * CH; c0 < BN; c0 += 2 * CH) {
+        for (int c0 = eg * CH; c0 < BN; c0 += NG * CH) {
           uint32_t raw[CH];
           if constexpr (CH == 32) tmem_ld_x32(taddr + c0, raw);
           else tmem_ld_x16(taddr + c0, raw);
@@ -357,11 +360,11 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
       const uint32_t row_off = static_cast<uint32_t>(r) * 64u;
       const uint32_t sw = (static_cast<uint32_t>(r) >> 1) & 3u;
 
-      // iterator over this warpgroup's chunks: chunk c of local tile lt belongs to group (lt*nchunk + c) & 1
+      // iterator over this warpgroup's chunks: chunk c of local tile lt belongs to group (lt*nchunk + c) % NG
       struct It {
         int tile, lt, c;
       };
-      auto first_c = [&](int lt_) { return (eg ^ (lt_ * nchunk)) & 1; };
+      auto first_c = [&](int lt_) { return ((eg - lt_ * nchunk) % NG + NG) % NG; };
       auto settle = [&](It& it) {  // skip tiles in which this group owns no chunk
         while (it.tile < num_tiles && it.c >= nchunk) {
           it.tile += nunits;
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         }
       };
       auto advance = [&](It& it) {
-        it.c += 2;
+        it.c += NG;
         settle(it);
       };
       auto coords = [&](const It& it, int& col, int& x0, int& y0, int& n0) {
@@ -424,26 +427,29 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
         const int c_first = first_c(lt);
 #pragma unroll 1
-        for (int c = c_first; c < nchunk; c += 2, ++k) {
+        for (int c = c_first; c < nchunk; c += NG, ++k) {
           const int b = k % NBG;
           uint8_t* buf = ring + b * IG_CHUNK_BYTES + row_off;
           uint32_t pk[16];  // 32 output halves
           if (p.geglu) {
-            uint32_t raw[64];
-            tmem_ld_x32(taddr + c * 64, raw);
-            tmem_ld_x32(taddr + c * 64 + 32, raw + 32);
-            tmem_wait_ld();
-            const float4* sb4 = reinterpret_cast<const float4*>(sbias + c * 64);
+            // 64 accumulator columns = (value, gate) x 32 outputs, drained in two 32-column TMEM reads
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              // accumulator columns 4i..4i+3 = (value, gate, value, gate) -> output columns 2i, 2i+1
-              float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias) bb = sb4[i];
-              const __half2 val = __floats2half2_rn(__uint_as_float(raw[4 * i]) + bb.x, __uint_as_float(raw[4 * i + 2]) + bb.z);
-              const __half2 gate = __floats2half2_rn(__uint_as_float(raw[4 * i + 1]) + bb.y, __uint_as_float(raw[4 * i + 3]) + bb.w);
-              const float2 gf = __half22float2(gate);
-              const __half2 act = __floats2half2_rn(gelu_fast(gf.x), gelu_fast(gf.y));
-              pk[i] = h2u(__hmul2(val, act));
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t raw[32];
+              tmem_ld_x32(taddr + c * 64 + hh * 32, raw);
+              tmem_wait_ld();
+              const float4* sb4 = reinterpret_cast<const float4*>(sbias + c * 64 + hh * 32);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                // accumulator columns 4i..4i+3 = (value, gate, value, gate) -> output columns 2i, 2i+1
+                float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias) bb = sb4[i];
+                const __half2 val = __floats2half2_rn(__uint_as_float(raw[4 * i]) + bb.x, __uint_as_float(raw[4 * i + 2]) + bb.z);
+                const __half2 gate = __floats2half2_rn(__uint_as_float(raw[4 * i + 1]) + bb.y, __uint_as_float(raw[4 * i + 3]) + bb.w);
+                const float2 gf = __half22float2(gate);
+                const __half2 act = __floats2half2_rn(gelu_fast(gf.x), gelu_fast(gf.y));
+                pk[hh * 8 + i] = h2u(__hmul2(val, act));
+              }
             }
           } else {
             uint32_t raw[32];
@@ -476,7 +482,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
               }
             }
           }
-          if (c + 2 >= nchunk) {  // last TMEM read of this tile by this warp: hand the accumulator back
+          if (c + NG >= nchunk) {  // last TMEM read of this tile by this warp: hand the accumulator back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {

@@ -60,7 +60,8 @@ static int env_or(const char* name, int dflt) {
 }
 static int variant_igemm_pair() { return g_igemm_pair >= 0 ? g_igemm_pair : env_or("DM_IGEMM_PAIR", 1); }
 static int variant_gn_fused() { return g_gn_fused >= 0 ? g_gn_fused : env_or("DM_GN_FUSED", 1); }
-static int g_xattn = -1, g_prefix = -1;
+static int g_xattn = -1, g_prefix = -1, g_ng4 = -1;
+static int variant_igemm_ng4() { return g_ng4 >= 0 ? g_ng4 : env_or("DM_IGEMM_NG4", 1); }
 int variant_prefix_share() { return g_prefix >= 0 ? g_prefix : env_or("DM_PREFIX_SHARE", 1); }
 static int variant_xattn() { return g_xattn >= 0 ? g_xattn : env_or("DM_XATTN", 1); }
 void set_variant(const std::string& name, int value) {
@@ -68,6 +69,7 @@ void set_variant(const std::string& name, int value) {
   else if (name == "gn_fused") g_gn_fused = value;
   else if (name == "xattn") g_xattn = value;
   else if (name == "prefix_share") g_prefix = value;
+  else if (name == "igemm_ng4") g_ng4 = value;
   else DM_CHECK(false, "unknown kernel variant '" + name + "'");
 }
 
@@ -206,27 +208,32 @@ IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms) {
     const uint32_t box[2] = {64, static_cast<uint32_t>(op.bn / op.cg)};  // a CTA of a pair loads half of the B tile
     make_tmap(&op.maps.b, d.Wt, 2, dims, st, box);
   }
+  // four epilogue warpgroups where the epilogue math bounds the tile: GEGLU with K = 320 (-14 % measured; the plain
+  // K = 320 / 640 Linears are HBM-bound and measured 2-5 % slower with four groups)
+  const int ng_mode = variant_igemm_ng4();
+  op.ng = (ng_mode && !op.direct && op.cg == 1 && (op.bn == 256 || op.bn == 160) &&
+           (ng_mode == 2 || (d.geglu && kit <= 5 && static_cast<long long>(p.m_tiles) * p.n_tiles >= 2 * num_sms))) ? 4 : 2;
   const int tiles = ((p.m_tiles + op.cg - 1) / op.cg) * p.n_tiles;
   op.grid = std::min(tiles, num_sms / op.cg) * op.cg;
   op.flops = 2.0 * d.Nimg * d.H * d.W * static_cast<double>(d.N) * d.K;
   return op;
 }
 
-template <int BN, bool DIRECT, int CG>
+template <int BN, bool DIRECT, int CG, int NG = 2>
 static void igemm_launch_bn(const IgemmOp& op, cudaStream_t s) {
   static bool configured = false;
-  using Cfg = IgCfg<BN, DIRECT, CG>;
+  using Cfg = IgCfg<BN, DIRECT, CG, NG>;
   if (!configured) {
-    DM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, DIRECT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    DM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, DIRECT, CG, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
   if (CG == 1) {
-    igemm_kernel<BN, DIRECT, CG><<<op.grid, IG_THREADS, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
+    igemm_kernel<BN, DIRECT, CG, NG><<<op.grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
     DM_CUDA(cudaGetLastError());
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(op.grid, 1, 1);
-    cfg.blockDim = dim3(IG_THREADS, 1, 1);
+    cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -236,7 +243,7 @@ static void igemm_launch_bn(const IgemmOp& op, cudaStream_t s) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DM_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<BN, DIRECT, CG>, op.maps, op.p));
+    DM_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<BN, DIRECT, CG, NG>, op.maps, op.p));
   }
 }
 
@@ -259,6 +266,14 @@ void igemm_launch(const IgemmOp& op, cudaStream_t s) {
       case 160: igemm_launch_bn<160, false, 2>(op, s); break;
       case 128: igemm_launch_bn<128, false, 2>(op, s); break;
       default: DM_CHECK(false, "igemm: unsupported BN " + std::to_string(op.bn) + " for CTA pairs");
+    }
+    return;
+  }
+  if (op.ng == 4) {
+    switch (op.bn) {
+      case 256: igemm_launch_bn<256, false, 1, 4>(op, s); break;
+      case 160: igemm_launch_bn<160, false, 1, 4>(op, s); break;
+      default: DM_CHECK(false, "igemm: unsupported BN " + std::to_string(op.bn) + " for four epilogue groups");
     }
     return;
   }

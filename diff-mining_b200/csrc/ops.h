@@ -63,6 +63,7 @@ struct IgemmOp {
   int bn = 0, grid = 0;
   int direct = 0;  // 1 = plain global-store epilogue (fp32 output or N-tile < 32 columns)
   int cg = 1;      // CTAs per tile (2 = CTA pair)
+  int ng = 2;      // epilogue warpgroups (4 for short-K, epilogue-bound layers)
   double flops = 0;
 };
 

@@ -121,6 +121,7 @@ int dm_op_layernorm(const void* x, int64_t rows, int C, const float* gamma, cons
 /* kernel-variant switches for tests / A-B timing (affect ops prepared afterwards; -1 = built-in default):
  *   igemm_pair  1 = CTA pairs (tcgen05 cta_group::2, 256-row tiles) where the problem is large enough, 0 = never,
  *               2 = wherever the tile shape allows (N-tile >= 128, fp16 output)
+ *   igemm_ng4   1 = four epilogue warpgroups for short-K (epilogue-bound) layers, 0 = always two, 2 = wherever possible
  *   gn_fused    1 = cluster-fused single-pass GroupNorm for images that fit in L2, 0 = two-kernel path
  *   xattn       1 = short-key-set cross-attention kernel (P in tensor memory), 0 = generic flash kernel
  *   prefix_share 1 = dm_typicality computes the context-free U-Net prefix once per (eps,t) draw (bit-identical) */

@@ -115,6 +115,19 @@ def test_conv_igemm_cta_pairs(lib, case):
         check(lib, lib.dm_op_set_variant(b"igemm_pair", -1))
 
 
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[5] >= 160 and not c[13] and c[14] in (0, 160, 256)],
+                         ids=lambda c: "-".join(map(str, c)))
+def test_conv_igemm_four_epilogue_groups(lib, case):
+    """same cases with four epilogue warpgroups (the short-K variant), forced for every eligible tile shape"""
+    check(lib, lib.dm_op_set_variant(b"igemm_pair", 0))
+    check(lib, lib.dm_op_set_variant(b"igemm_ng4", 2))
+    try:
+        test_conv_igemm(lib, case)
+    finally:
+        check(lib, lib.dm_op_set_variant(b"igemm_ng4", -1))
+        check(lib, lib.dm_op_set_variant(b"igemm_pair", -1))
+
+
 def test_groupnorm_two_kernel_path_matches_fused(lib):
     """the cluster-fused GroupNorm and the stats + apply path agree (both deterministic)"""
     g = torch.Generator(device="cuda").manual_seed(7)
