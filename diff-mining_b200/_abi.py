@@ -42,6 +42,8 @@ SIGNATURES = {
     "dm_op_groupnorm": (I, [P, P, I, I, I, I, P, P, F, I, P, P]),
     "dm_op_layernorm": (I, [P, L, I, P, P, F, P, P]),
     "dm_op_set_variant": (I, [ctypes.c_char_p, I]),
+    "dm_patch_topk": (I, [P, I, I, I, I, I, I, I, I, I, P, P, P, P, P]),
+    "dm_patch_topk_work_floats": (L, [I, I, I, I]),
 }
 
 _lib = None

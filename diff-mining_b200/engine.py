@@ -53,6 +53,21 @@ class Engine:
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def patch_topk(self, T: torch.Tensor, H: int, W: int, kx: int = 64, ky: int = 64, k: int = 5, descending: bool = True):
+        """The reference's T-map consumer on the GPU (cluster.py:125-137,183-205; utils.py:74-102): T [B,h,w] fp32
+        (one condition of `typicality()`'s T output) -> bilinear resize to H x W -> kx x ky average pooling -> the k
+        best mutually non-overlapping windows.  Returns (boxes int32 [B,k,4] = x_start, y_start, x_end, y_end in the
+        reference's (row, column) convention, scores fp32 [B,k], count int32 [B]) on the device."""
+        T = T.to(self.device, torch.float32).contiguous()
+        B, h, w = T.shape
+        work = torch.empty(int(self.lib.dm_patch_topk_work_floats(B, H, W, ky)), device=self.device, dtype=torch.float32)
+        boxes = torch.zeros(B, k, 4, device=self.device, dtype=torch.int32)
+        scores = torch.zeros(B, k, device=self.device, dtype=torch.float32)
+        count = torch.zeros(B, device=self.device, dtype=torch.int32)
+        _abi.check(self.lib.dm_patch_topk(_ptr(T), B, h, w, H, W, kx, ky, k, 1 if descending else 0, _ptr(work), _ptr(boxes),
+                                          _ptr(scores), _ptr(count), self._stream()))
+        return boxes, scores, count
+
     def set_variant(self, name: str, value: int) -> None:
         """kernel-variant switch for tests / A-B timing (process-wide; -1 = default): "igemm_pair", "gn_fused", "xattn",
         "prefix_share" (include/dm_abi.h: dm_op_set_variant).  Plans built earlier keep the variant they were built with."""

@@ -103,6 +103,17 @@ int64_t dm_debug_fetch(dm_engine* e, const char* name, float* out_dev, int64_t c
 int dm_profile_unet(dm_engine* e, int Bf, int h, int w, int iters, double* ms_igemm, double* ms_attn, double* ms_other,
                     double* flops_igemm, double* flops_attn);
 
+/* ---- T-map consumer: replaces Cluster.load_typicality + df_D + get_non_overlapping
+ * (cluster.py:125-137,183-205; utils.py:74-102) for the engine's own T maps.  T: DEVICE fp32 [B,h,w] (dm_typicality
+ * output, one condition); the map is resized bilinearly (align_corners=False) to H x W, average-pooled with a kx x ky
+ * window (stride 1, valid) and the k best mutually non-overlapping windows are kept (descending != 0: highest scores
+ * first).  work: DEVICE fp32 scratch of dm_patch_topk_work_floats() elements.  Outputs (DEVICE): boxes int32 [B,k,4] =
+ * (x_start, y_start, x_end, y_end) in the reference's (row, column) convention with x_end = x_start + kx, scores fp32
+ * [B,k], count int32 [B] (windows actually found). */
+int dm_patch_topk(const float* T, int B, int h, int w, int H, int W, int kx, int ky, int k, int descending, float* work,
+                  int32_t* boxes, float* scores, int32_t* count, void* stream);
+int64_t dm_patch_topk_work_floats(int B, int H, int W, int ky);
+
 /* ---- operator-level entry points (unit tests / debugging; same kernels the engine uses) ------------------ */
 /* conv / linear as implicit GEMM.  x,x2: DEVICE fp16 NHWC [N,H,W,C0|C1] (x2 may be NULL); w: DEVICE fp16
  * [Cout, ks*ks*(C0+C1)] tap-major; bias DEVICE fp32 [Cout] or NULL; rowbias DEVICE fp16 [N,Cout] or NULL;

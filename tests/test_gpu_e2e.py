@@ -151,6 +151,38 @@ def test_typicality_prefix_sharing_is_bit_identical(engine):
         assert torch.equal(out[(1, n_cond)][0], out[(0, n_cond)][0]) and torch.equal(out[(1, n_cond)][1], out[(0, n_cond)][1])
 
 
+@pytest.mark.parametrize("Bi,N,h,w,kx,k", [(2, 3, 16, 16, 24, 5), (1, 2, 12, 20, 16, 8), (2, 2, 8, 8, 64, 3)])
+def test_patch_topk_matches_reference_consumer(engine, Bi, N, h, w, kx, k):
+    """T-map consumer: engine.typicality -> engine.patch_topk against the restated cluster.py
+    load_typicality + df_D + get_non_overlapping run on the SAME raw fp16 loss grid"""
+    from oracle import consumers
+
+    g = torch.Generator().manual_seed(31 + h)
+    x0 = torch.randn(Bi, 4, h, w, generator=g)
+    noise = torch.randn(N, 4, h, w, generator=g)
+    t = torch.randint(100, 700, (N,), generator=g)
+    grid, T = engine.typicality(x0, noise, t, [1, 0])   # condition, unconditional
+    H, W = 8 * h, 8 * w
+    boxes, scores, count = engine.patch_topk(T[:, 0], H, W, kx, kx, k)
+    torch.cuda.synchronize()
+    for i in range(Bi):
+        D = consumers.patch_scores(grid[i].cpu().numpy(), H, W, kx, kx)
+        ref = consumers.non_overlapping_topk(D, kx, kx, k)
+        n = int(count[i])
+        assert n == len(ref)
+        got = boxes[i, :n].cpu().tolist()
+        sc = scores[i, :n].cpu().numpy()
+        scale = np.abs(D).max()
+        for r, bx, s_ in zip(ref, got, sc):
+            # same window, or (fp32 summation order differs) a window whose reference score is within rounding of it
+            assert abs(D[bx[0], bx[1]] - r[4]) <= 1e-4 * scale, (r, bx)
+            assert bx[2] == bx[0] + kx and bx[3] == bx[1] + kx
+            assert abs(s_ - D[bx[0], bx[1]]) <= 1e-4 * scale  # fp32 sums over kx*ky*N terms in a different order
+        for a in range(n):
+            for b in range(a):
+                assert abs(got[a][0] - got[b][0]) > kx or abs(got[a][1] - got[b][1]) > kx
+
+
 def test_typicality_properties_full_size(engine):
     """BASELINE config-2 latent size (64x64): size-independent properties instead of an oracle run"""
     Bi, N, h, w = 2, 4, 64, 64

@@ -111,3 +111,34 @@ def test_synthetic_weights_are_fp16_representable(unet_weights):
     for k in ("conv_in.weight", "mid_block.resnets.0.conv1.weight", "conv_out.bias"):
         w = unet_weights[k]
         assert torch.equal(w, w.half().float())
+
+
+def test_consumer_oracle_matches_pandas_restatement():
+    """oracle/consumers.py against a literal pandas transcription of df_D + get_non_overlapping (cluster.py:193-204,
+    utils.py:83-102) on a small random loss grid"""
+    import pandas as pd
+
+    from oracle import consumers
+
+    rng = np.random.default_rng(0)
+    grid = rng.random((3, 2, 4, 6, 7)).astype(np.float16)
+    H, W, kx, ky, k = 48, 56, 8, 8, 5
+    D = consumers.patch_scores(grid, H, W, kx, ky)
+    assert D.shape == (H - kx + 1, W - ky + 1)
+    df = pd.DataFrame([(i, j, i + kx, j + ky, D[i, j]) for i in range(D.shape[0]) for j in range(D.shape[1])],
+                      columns=["x_start", "y_start", "x_end", "y_end", "D"])
+    df = df.sort_values(by=["D"], ascending=False, kind="stable").reset_index(drop=True)
+    picked = []
+    while len(picked) < k:
+        picked.append(df.iloc[0])
+        last = picked[-1]
+        df = df[~((df["x_start"] <= last["x_end"]) & (df["x_end"] >= last["x_start"]) & (df["y_start"] <= last["y_end"])
+                  & (df["y_end"] >= last["y_start"]))].reset_index(drop=True)
+        if df.shape[0] == 0:
+            break
+    ours = consumers.non_overlapping_topk(D, kx, ky, k)
+    assert [(int(r["x_start"]), int(r["y_start"])) for r in picked] == [(r[0], r[1]) for r in ours]
+    # boxes are mutually non-overlapping under the inclusive test
+    for a in range(len(ours)):
+        for b in range(a):
+            assert abs(ours[a][0] - ours[b][0]) > kx or abs(ours[a][1] - ours[b][1]) > ky
