@@ -70,7 +70,12 @@ void check_slots(const int32_t* slots, int n) {
     DM_CHECK(slots[i] >= 0 && slots[i] < kMaxCtxSlots, "context slot out of range");
 }
 
-constexpr int kDefaultMaxForwards = 32;
+// default micro-batch cap: 56 forwards at 64x64 latents (fills the 148 SMs at every U-Net level),
+// scaled down with the latent area so the plan arena stays a few GB at 128x128
+inline int default_max_forwards(int h, int w) {
+  const long long cap = 56ll * 4096 / std::max(1ll, static_cast<long long>(h) * w);
+  return static_cast<int>(std::max(8ll, std::min(56ll, cap)));
+}
 
 }  // namespace
 
@@ -176,7 +181,7 @@ extern "C" int dm_unet_rows(dm_engine* h, const float* x, const float* noise, co
     }
     int* dev = ensure_idx(h, host.size());
     DM_CUDA(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-    const int Bf = std::min(M, max_forwards > 0 ? max_forwards : kDefaultMaxForwards);
+    const int Bf = std::min(M, max_forwards > 0 ? max_forwards : default_max_forwards(hh, ww));
     const int HW = hh * ww;
     for (int m0 = 0; m0 < M; m0 += Bf) {
       const int nb = std::min(Bf, M - m0);
@@ -237,7 +242,7 @@ extern "C" int dm_typicality(dm_engine* h, const float* x0, const float* noise, 
     __half* grid = grid_out ? static_cast<__half*>(grid_out) : ensure_grid(h, static_cast<size_t>(F) * 4 * HW);
     // balanced micro-batches: as few as the cap allows, equal sizes (whole (eps,t) draws: multiples of n_cond), so no
     // small remainder batch under-fills the 148 SMs
-    const long long want = max_forwards > 0 ? max_forwards : kDefaultMaxForwards;
+    const long long want = max_forwards > 0 ? max_forwards : default_max_forwards(hh, ww);
     const long long cap = std::max<long long>(n_cond, want / n_cond * n_cond);  // whole draws only
     const long long n_mb = (F + cap - 1) / cap;
     const int Bf = static_cast<int>(((F + n_mb - 1) / n_mb + n_cond - 1) / n_cond * n_cond);
