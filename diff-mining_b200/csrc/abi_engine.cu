@@ -351,7 +351,10 @@ extern "C" int dm_profile_unet(dm_engine* h, int Bf, int hh, int ww, int iters, 
   return abi_guard([&] {
     DM_CHECK(h && iters > 0, "dm_profile_unet: bad arguments");
     Engine& e = h->eng;
-    Plan* p = e.get_plan(PlanKey{kPlanUnet, Bf, hh, ww, 0});
+    // DM_PROFILE_KIND=vae profiles the VAE-encoder plan instead (hh, ww = image size): development aid
+    const char* kind_env = getenv("DM_PROFILE_KIND");
+    const int kind = (kind_env && std::string(kind_env) == "vae") ? kPlanVae : kPlanUnet;
+    Plan* p = e.get_plan(PlanKey{kind, Bf, hh, ww, 0});
     cudaStream_t s = e.cap_stream;
     const size_t n = p->steps.size();
     std::vector<cudaEvent_t> ev(n + 1);

@@ -127,6 +127,8 @@ def layers():
     usd = sd15.make_synthetic_weights(sd15.unet_param_shapes(), seed=0)
     eng = Engine(0)
     eng.load_state_dict(usd, "unet.")
+    if os.environ.get("DM_PROFILE_KIND") == "vae":  # DM_LAT = image size then
+        eng.load_state_dict(sd15.make_synthetic_weights(sd15.vae_encoder_param_shapes(), seed=1), "vae.")
     eng.finalize()
     g = torch.Generator().manual_seed(5)
     for i in range(2):
