@@ -101,7 +101,9 @@ __global__ void __launch_bounds__(640, 1) attention2_kernel(const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 256, head = blockIdx.y, b = blockIdx.z;
+  // batches in reverse launch order: the qkv GEMM that ran just before wrote the highest batch indices last, so
+  // those rows are still L2-resident when the first CTAs start
+  const int q0 = blockIdx.x * 256, head = blockIdx.y, b = static_cast<int>(gridDim.z) - 1 - static_cast<int>(blockIdx.z);
   const int kvb = p.kv_index ? p.kv_index[b] : b;
   const int nkv = (p.Tk + BKV - 1) / BKV;
 
@@ -121,9 +123,16 @@ __global__ void __launch_bounds__(640, 1) attention2_kernel(const __grid_constan
       mbar_init(&o_full[2 * i + 1], 1);
     }
     fence_barrier_init();
-    tma_prefetch_desc(&maps.q);
-    tma_prefetch_desc(&maps.k);
-    tma_prefetch_desc(&maps.v);
+    // this thread is also the TMA producer: start the Q / first K / first V loads before the TMEM allocation and the
+    // CTA-wide sync, their latency (>= 2000 cycles on a cold tile) is the longest part of the prologue
+    mbar_arrive_expect_tx(q_full, 2 * Cfg::Q_TILE_BYTES);
+    for (int qq = 0; qq < 2; ++qq)
+      for (int c = 0; c < NCH; ++c)
+        tma_load_4d(sQ + qq * Cfg::Q_TILE_BYTES + c * 16384, &maps.q, q_full, c * 64, head, q0 + qq * 128, b);
+    mbar_arrive_expect_tx(&k_full[0], Cfg::KV_BYTES);
+    for (int c = 0; c < NCH; ++c) tma_load_4d(sK + c * BKV * 128, &maps.k, &k_full[0], c * 64, head, 0, kvb);
+    mbar_arrive_expect_tx(&v_full[0], Cfg::KV_BYTES);
+    for (int c = 0; c < NCH; ++c) tma_load_4d(sV + c * BKV * 128, &maps.v, &v_full[0], c * 64, head, 0, kvb);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -137,11 +146,7 @@ __global__ void __launch_bounds__(640, 1) attention2_kernel(const __grid_constan
   if (warp == 0) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, 2 * Cfg::Q_TILE_BYTES);
-      for (int qq = 0; qq < 2; ++qq)
-        for (int c = 0; c < NCH; ++c)
-          tma_load_4d(sQ + qq * Cfg::Q_TILE_BYTES + c * 16384, &maps.q, q_full, c * 64, head, q0 + qq * 128, b);
-      for (int j = 0; j < nkv; ++j) {
+      for (int j = 1; j < nkv; ++j) {  // Q and tile 0 were issued in the prologue
         const int st = j % ST;
         const uint32_t ph = (j / ST) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
