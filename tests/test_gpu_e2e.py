@@ -183,6 +183,32 @@ def test_patch_topk_matches_reference_consumer(engine, Bi, N, h, w, kx, k):
                 assert abs(got[a][0] - got[b][0]) > kx or abs(got[a][1] - got[b][1]) > kx
 
 
+def test_typicality_xray_configuration(engine, contexts):
+    """BASELINE config 5 shapes: 1024x1024 image (128x128 latents, 16384-token self-attention), 14 conditions + the
+    unconditional slot batched in one call -- size-independent properties"""
+    g = torch.Generator().manual_seed(9)
+    for s_ in range(3, 15):
+        engine.set_context(s_, torch.randn(77, 768, generator=g))
+    x0 = torch.randn(1, 4, 128, 128, generator=g)
+    noise = torch.randn(2, 4, 128, 128, generator=g)
+    t = torch.tensor([100, 900])
+    slots = list(range(1, 15)) + [0]
+    grid, T = engine.typicality(x0, noise, t, slots)
+    assert grid.shape == (1, 2, 15, 4, 128, 128) and T.shape == (1, 14, 128, 128)
+    assert torch.isfinite(grid.float()).all() and float(grid.float().min()) >= 0.0
+    # T of condition k == mean over draws of channel-mean(uncond - cond_k) of the fp16 grid
+    g16 = grid.float()
+    Tk = (g16[:, :, 14].mean(2) - g16[:, :, 5].mean(2)).mean(1)
+    torch.testing.assert_close(T[:, 5], Tk, atol=2e-6, rtol=1e-5)
+    # the 15-way shared prefix changes no bit
+    engine.set_variant("prefix_share", 0)
+    try:
+        grid2, _ = engine.typicality(x0, noise, t, slots)
+    finally:
+        engine.set_variant("prefix_share", -1)
+    assert torch.equal(grid, grid2)
+
+
 def test_typicality_properties_full_size(engine):
     """BASELINE config-2 latent size (64x64): size-independent properties instead of an oracle run"""
     Bi, N, h, w = 2, 4, 64, 64
