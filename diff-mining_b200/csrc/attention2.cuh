@@ -286,8 +286,8 @@ __global__ void __launch_bounds__(640, 1) attention2_kernel(const __grid_constan
         }
         tmem_wait_st();
       }
-      // P buffer j&1 was last read by PV(j-2)
-      if (j >= 2) mbar_wait(&o_full_q[jp], ((j - 2) >> 1) & 1);
+      // P buffer j&1 was last read by PV(j-2).  No wait is needed: this thread observed s_full(j), i.e. the completion
+      // of QK(j), and tcgen05.commit tracks ALL earlier MMAs of the issuing thread -- PV(j-2) was issued before QK(j).
       {
         float la, lb;
         unpack_f2(l2, la, lb);
