@@ -23,6 +23,20 @@ struct dm_engine {
 
 namespace {
 
+// Every engine entry point runs on the engine's device (function attributes, arenas and plans are per device) and
+// restores the caller's current device on exit.
+struct DeviceScope {
+  int prev = -1;
+  explicit DeviceScope(int dev) {
+    DM_CUDA(cudaGetDevice(&prev));
+    if (prev != dev) DM_CUDA(cudaSetDevice(dev));
+    else prev = -1;
+  }
+  ~DeviceScope() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 int* ensure_idx(dm_engine* h, size_t n) {
   if (h->idx_cap < n) {
     if (h->idx_dev) cudaFree(h->idx_dev);
@@ -56,7 +70,8 @@ Plan* unet_microbatch(Engine& e, int kind, int aux, const float* x, const int* x
   Plan* p = e.get_plan(PlanKey{kind, Bf, h, w, aux});
   // kPlanUnet with aux = G > 1: the input patch matrix is built once per group of G forwards sharing (x_t, t)
   const int G = (kind == kPlanUnet && aux > 1) ? aux : 1;
-  patch3x3_launch(x, x_index, noise, noise_index, t, e.sched_a, e.sched_b, Bf / G, 4, h, w, p->a_in, s, G);
+  patch3x3_launch(x, x_index, noise, noise_index, t, e.sched_a, e.sched_b, Bf / G, 4, h, w, p->a_in, s, G, e.sched_n,
+                  e.err_dev);
   timestep_embed_launch(t, t_index, Bf, p->temb_sin, s);
   DM_CUDA(cudaMemcpyAsync(p->ctx_idx, ctx_idx, Bf * sizeof(int), cudaMemcpyDeviceToDevice, s));
   e.launch_count += 2;
@@ -120,18 +135,21 @@ extern "C" int dm_load_tensor(dm_engine* h, const char* key, const void* host_pt
 extern "C" int dm_finalize_weights(dm_engine* h) {
   return abi_guard([&] {
     DM_CHECK(h, "null engine");
+    DeviceScope dev_scope(h->eng.device);
     h->eng.finalize();
   });
 }
 extern "C" int dm_set_schedule(dm_engine* h, const float* a, const float* b, int n) {
   return abi_guard([&] {
     DM_CHECK(h, "null engine");
+    DeviceScope dev_scope(h->eng.device);
     h->eng.set_schedule(a, b, n);
   });
 }
 extern "C" int dm_set_context(dm_engine* h, int slot, const float* ctx, void* stream) {
   return abi_guard([&] {
     DM_CHECK(h && ctx, "dm_set_context: null argument");
+    DeviceScope dev_scope(h->eng.device);
     h->eng.set_context(slot, ctx, static_cast<cudaStream_t>(stream));
   });
 }
@@ -140,6 +158,8 @@ extern "C" int dm_vae_encode(dm_engine* h, const float* img, const float* eps, i
                              float* logvar, void* stream) {
   return abi_guard([&] {
     DM_CHECK(h && img, "dm_vae_encode: null argument");
+    DeviceScope dev_scope(h->eng.device);
+    h->eng.check_async_error();
     DM_CHECK(B > 0 && H >= 8 && W >= 8, "dm_vae_encode: empty batch or image smaller than 8x8");
     Engine& e = h->eng;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -168,6 +188,8 @@ extern "C" int dm_unet_rows(dm_engine* h, const float* x, const float* noise, co
                             float* loss_out, float* eps_out, int max_forwards, void* stream) {
   return abi_guard([&] {
     DM_CHECK(h && x && t && ctx_slots, "dm_unet_rows: null argument");
+    DeviceScope dev_scope(h->eng.device);
+    h->eng.check_async_error();
     DM_CHECK(M > 0 && hh > 0 && ww > 0, "dm_unet_rows: empty problem");
     DM_CHECK(noise || !loss_out, "dm_unet_rows: a loss needs the noise");
     Engine& e = h->eng;
@@ -218,6 +240,8 @@ extern "C" int dm_typicality(dm_engine* h, const float* x0, const float* noise, 
                              float* T_out, int max_forwards, void* stream) {
   return abi_guard([&] {
     DM_CHECK(h && x0 && noise && t && ctx_slots, "dm_typicality: null argument");
+    DeviceScope dev_scope(h->eng.device);
+    h->eng.check_async_error();
     DM_CHECK(Bi > 0 && N > 0 && n_cond > 0 && hh > 0 && ww > 0, "dm_typicality: empty problem");
     DM_CHECK(grid_out || T_out, "dm_typicality: no output requested");
     DM_CHECK(!T_out || n_cond >= 2, "dm_typicality: T(x|c) needs a condition and the unconditional slot");
@@ -280,6 +304,8 @@ extern "C" int dm_dift(dm_engine* h, const float* latents, const float* noise, i
                        int hh, int ww, int up_ft_index, float* feat_out, void* stream) {
   return abi_guard([&] {
     DM_CHECK(h && latents && feat_out, "dm_dift: null argument");
+    DeviceScope dev_scope(h->eng.device);
+    h->eng.check_async_error();
     DM_CHECK(B > 0 && E > 0, "dm_dift: empty batch");
     DM_CHECK(up_ft_index >= 0 && up_ft_index <= 2, "dm_dift: up_ft_index must be 0, 1 or 2");
     DM_CHECK(t >= 0 && t < h->eng.sched_n, "dm_dift: timestep out of range");
@@ -329,6 +355,7 @@ extern "C" int64_t dm_debug_fetch(dm_engine* h, const char* name, float* out_dev
   int64_t n = -1;
   int rc = abi_guard([&] {
     DM_CHECK(h && name, "null argument");
+    DeviceScope dev_scope(h->eng.device);
     Plan* p = h->eng.last_unet_plan;
     DM_CHECK(p != nullptr, "no U-Net forward has run with dm_debug_keep(1)");
     auto it = p->taps.find(name);
@@ -346,47 +373,65 @@ extern "C" int64_t dm_debug_fetch(dm_engine* h, const char* name, float* out_dev
   return rc == 0 ? n : -1;
 }
 
+namespace {
+void profile_plan(Engine& e, PlanKey key, int iters, double* ms_igemm, double* ms_attn, double* ms_other,
+                  double* flops_igemm, double* flops_attn) {
+  Plan* p = e.get_plan(key);
+  cudaStream_t s = e.cap_stream;
+  const size_t n = p->steps.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& x : ev) DM_CUDA(cudaEventCreate(&x));
+  for (auto& st : p->steps) st.run(s);  // warm-up
+  DM_CUDA(cudaStreamSynchronize(s));
+  double acc[3] = {0, 0, 0};
+  const bool verbose = getenv("DM_PROFILE_VERBOSE") != nullptr;
+  std::vector<double> per(n, 0.0);
+  for (int it = 0; it < iters; ++it) {
+    DM_CUDA(cudaEventRecord(ev[0], s));
+    for (size_t i = 0; i < n; ++i) {
+      p->steps[i].run(s);
+      DM_CUDA(cudaEventRecord(ev[i + 1], s));
+    }
+    DM_CUDA(cudaStreamSynchronize(s));
+    for (size_t i = 0; i < n; ++i) {
+      float ms = 0;
+      DM_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      acc[p->steps[i].cls] += ms;
+      per[i] += ms;
+    }
+  }
+  if (verbose)
+    for (size_t i = 0; i < n; ++i)
+      printf("DMPROF %-70s cls=%d ms=%.4f gflop=%.2f\n", p->steps[i].name.c_str(), p->steps[i].cls, per[i] / iters,
+             p->steps[i].flops * 1e-9);
+  for (auto& x : ev) cudaEventDestroy(x);
+  if (ms_igemm) *ms_igemm = acc[0] / iters;
+  if (ms_attn) *ms_attn = acc[1] / iters;
+  if (ms_other) *ms_other = acc[2] / iters;
+  if (flops_igemm) *flops_igemm = p->flops_igemm;
+  if (flops_attn) *flops_attn = p->flops_attn;
+}
+}  // namespace
+
 extern "C" int dm_profile_unet(dm_engine* h, int Bf, int hh, int ww, int iters, double* ms_igemm, double* ms_attn,
                                double* ms_other, double* flops_igemm, double* flops_attn) {
   return abi_guard([&] {
     DM_CHECK(h && iters > 0, "dm_profile_unet: bad arguments");
-    Engine& e = h->eng;
+    DeviceScope dev_scope(h->eng.device);
     // DM_PROFILE_KIND=vae profiles the VAE-encoder plan instead (hh, ww = image size): development aid
     const char* kind_env = getenv("DM_PROFILE_KIND");
     const int kind = (kind_env && std::string(kind_env) == "vae") ? kPlanVae : kPlanUnet;
-    Plan* p = e.get_plan(PlanKey{kind, Bf, hh, ww, 0});
-    cudaStream_t s = e.cap_stream;
-    const size_t n = p->steps.size();
-    std::vector<cudaEvent_t> ev(n + 1);
-    for (auto& x : ev) DM_CUDA(cudaEventCreate(&x));
-    for (auto& st : p->steps) st.run(s);  // warm-up
-    DM_CUDA(cudaStreamSynchronize(s));
-    double acc[3] = {0, 0, 0};
-    const bool verbose = getenv("DM_PROFILE_VERBOSE") != nullptr;
-    std::vector<double> per(n, 0.0);
-    for (int it = 0; it < iters; ++it) {
-      DM_CUDA(cudaEventRecord(ev[0], s));
-      for (size_t i = 0; i < n; ++i) {
-        p->steps[i].run(s);
-        DM_CUDA(cudaEventRecord(ev[i + 1], s));
-      }
-      DM_CUDA(cudaStreamSynchronize(s));
-      for (size_t i = 0; i < n; ++i) {
-        float ms = 0;
-        DM_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
-        acc[p->steps[i].cls] += ms;
-        per[i] += ms;
-      }
-    }
-    if (verbose)
-      for (size_t i = 0; i < n; ++i)
-        printf("DMPROF %-70s cls=%d ms=%.4f gflop=%.2f\n", p->steps[i].name.c_str(), p->steps[i].cls, per[i] / iters,
-               p->steps[i].flops * 1e-9);
-    for (auto& x : ev) cudaEventDestroy(x);
-    if (ms_igemm) *ms_igemm = acc[0] / iters;
-    if (ms_attn) *ms_attn = acc[1] / iters;
-    if (ms_other) *ms_other = acc[2] / iters;
-    if (flops_igemm) *flops_igemm = p->flops_igemm;
-    if (flops_attn) *flops_attn = p->flops_attn;
+    profile_plan(h->eng, PlanKey{kind, Bf, hh, ww, 0}, iters, ms_igemm, ms_attn, ms_other, flops_igemm, flops_attn);
+  });
+}
+
+extern "C" int dm_profile_plan(dm_engine* h, int kind, int Bf, int hh, int ww, int aux, int iters, double* ms_by_class,
+                               double* flops_by_class) {
+  return abi_guard([&] {
+    DM_CHECK(h && iters > 0 && ms_by_class && flops_by_class, "dm_profile_plan: bad arguments");
+    DM_CHECK(kind == kPlanUnet || kind == kPlanDift || kind == kPlanVae, "dm_profile_plan: kind must be 0 (U-Net), 1 (DIFT) or 2 (VAE)");
+    DeviceScope dev_scope(h->eng.device);
+    profile_plan(h->eng, PlanKey{kind, Bf, hh, ww, aux}, iters, &ms_by_class[0], &ms_by_class[1], &ms_by_class[2],
+                 &flops_by_class[0], &flops_by_class[1]);
   });
 }

@@ -105,7 +105,7 @@ extern "C" int dm_op_groupnorm(const void* x, const void* x2, int N, int HW, int
     d.Nimg = N; d.HW = HW; d.gamma = gamma; d.beta = beta; d.eps = eps; d.silu = silu;
     d.out = static_cast<__half*>(out);
     float* partial = nullptr;
-    const size_t n_part = 64ull * N * gn_splits(N, HW), n_ab = 2ull * N * (C0 + d.C1);
+    const size_t n_part = 2ull * (C0 + d.C1) * N * gn_splits(N, HW), n_ab = 2ull * N * (C0 + d.C1);
     DM_CUDA(cudaMalloc(&partial, sizeof(float) * (n_part + n_ab) + sizeof(unsigned) * N));
     d.partial = partial;
     d.ab = partial + n_part;

@@ -63,6 +63,7 @@ Plan::~Plan() {
 Engine::~Engine() {
   plans.clear();
   for (void* p : owned) cudaFree(p);
+  if (err_host) cudaFreeHost(err_host);
   if (cap_stream) cudaStreamDestroy(cap_stream);
 }
 
@@ -368,8 +369,19 @@ void Engine::finalize() {
     set_schedule(a.data(), b.data(), 1000);
   }
   DM_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+  DM_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&err_host), sizeof(int), cudaHostAllocMapped));
+  *err_host = 0;
+  DM_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&err_dev), err_host, 0));
   DM_CUDA(cudaDeviceSynchronize());
   finalized = true;
+}
+
+void Engine::check_async_error() {
+  if (err_host && *reinterpret_cast<volatile int*>(err_host) != 0) {
+    *err_host = 0;
+    DM_CHECK(false, "an earlier call on this engine used timesteps outside [0, " + std::to_string(sched_n) +
+                        ") (they were clamped on the device; its results are invalid)");
+  }
 }
 
 void Engine::set_schedule(const float* a, const float* b, int n) {

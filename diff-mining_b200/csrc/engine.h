@@ -114,6 +114,11 @@ struct Engine {
   int64_t launch_count = 0;
   double flop_count = 0;
   bool has_unet = false, has_vae = false;
+  // sticky device-side error flag (zero-copy pinned host word): set by kernels that had to clamp an out-of-range
+  // timestep; reported by the next ABI call on this engine
+  int* err_host = nullptr;
+  int* err_dev = nullptr;
+  void check_async_error();
 
   ~Engine();
   void* dmalloc(size_t bytes);

@@ -15,8 +15,9 @@ __global__ void __launch_bounds__(256) patch3x3_kernel(const float* __restrict__
                                                        const float* __restrict__ noise,
                                                        const int* __restrict__ noise_index,
                                                        const long long* __restrict__ t, const float* __restrict__ ca,
-                                                       const float* __restrict__ cb, int Bf, int Cin, int H, int W,
-                                                       int index_stride, __half* __restrict__ out) {
+                                                       const float* __restrict__ cb, int sched_n, int* err_flag,
+                                                       int Bf, int Cin, int H, int W, int index_stride,
+                                                       __half* __restrict__ out) {
   const long long total = static_cast<long long>(Bf) * H * W * 8;  // 8 x 16-byte vectors per row
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -28,7 +29,11 @@ __global__ void __launch_bounds__(256) patch3x3_kernel(const float* __restrict__
     const int ni = noise_index ? noise_index[b * index_stride] : b;
     float a = 1.f, bb = 0.f;
     if (noise) {
-      const long long tt = t[ni];
+      long long tt = t[ni];
+      if (tt < 0 || tt >= sched_n) {  // never index the schedule tables out of bounds; the host reports the sticky flag
+        if (err_flag) *err_flag = 1;
+        tt = tt < 0 ? 0 : sched_n - 1;
+      }
       a = ca[tt];
       bb = cb[tt];
     }

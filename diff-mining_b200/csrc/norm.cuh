@@ -26,82 +26,138 @@ __device__ __forceinline__ const __half* norm_src_ptr(const NormSrc& s0, const N
   return first ? s0.ptr + c : s1.ptr + (c - s0.C);
 }
 
-// Pass 1.  grid (splits, Nimg), block >= max(256, VT*R) threads: thread (r, vt), r < R, owns channel vector vt and pixels
-// p0+r, p0+r+R, ... of this split.  partial[n][split][g] = (sum, sumsq); the LAST block of an image
-// (atomic ticket) folds the splits in index order and writes the per-(image, channel) affine
-// ab[n][c] = (gamma*rstd, beta - mean*gamma*rstd).  Deterministic: fixed per-thread pixel sequence, fixed
+// ---- numerically stable statistics.  var = E[x^2] - E[x]^2 cancels when |mean| >> std (real SD-1.5 activations have
+// large-mean channels), so every sum is taken about a per-(image, channel) shift k_c = x[n, pixel 0, c]:
+//   S_c = sum (x - k_c),  Q_c = sum (x - k_c)^2            (per thread -> per CTA -> per image, fixed order)
+//   mean_g = sum_{c in g} (S_c + n k_c) / (n cpg)
+//   M2_g   = sum_{c in g} [ Q_c - 2 d_c S_c + n d_c^2 ],  d_c = mean_g - k_c      (= sum (x - mean_g)^2 exactly)
+// which is as stable as the Welford update torch's group_norm uses.  All threads / CTAs / splits of an image use the
+// same k_c, so the combination stays a plain fixed-order sum: deterministic and batch-invariant as before.
+__device__ __forceinline__ void gn_unpack8(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 v = __half22float2(h[i]);
+    f[2 * i] = v.x;
+    f[2 * i + 1] = v.y;
+  }
+}
+
+// per-thread shifted sums over pixels p0+r, p0+r+R, ... < p1 of one channel vector (UNR independent loads in flight)
+template <int UNR>
+__device__ __forceinline__ void gn_accumulate(const __half* base, long long ps, int p0, int p1, int r, int R,
+                                              const float (&k)[8], float (&a)[8], float (&q)[8]) {
+  auto acc = [&](const uint4& u) {
+    float f[8];
+    gn_unpack8(u, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float d = f[i] - k[i];
+      a[i] += d;
+      q[i] = fmaf(d, d, q[i]);
+    }
+  };
+  int px = p0 + r;
+  for (; px + (UNR - 1) * R < p1; px += UNR * R) {
+    uint4 u[UNR];
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) u[j] = __ldg(reinterpret_cast<const uint4*>(base + (px + j * R) * ps));
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) acc(u[j]);
+  }
+  for (; px < p1; px += R) acc(__ldg(reinterpret_cast<const uint4*>(base + px * ps)));
+}
+
+// shared memory layout of the GroupNorm kernels: [R*C] S | [R*C] Q | [C] shifts   (floats)
+__host__ __device__ inline size_t gn_smem_floats(int VT, int R) { return static_cast<size_t>(VT) * 8 * (2 * R + 1); }
+
+// fold the per-thread sums of a CTA into per-channel totals (left in row 0 of sm_a / sm_q).  Caller syncs after.
+__device__ __forceinline__ void gn_fold_channels(float* sm_a, float* sm_q, int C, int R) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f, qq = 0.f;
+    for (int rr = 0; rr < R; ++rr) {
+      s += sm_a[rr * C + c];
+      qq += sm_q[rr * C + c];
+    }
+    sm_a[c] = s;
+    sm_q[c] = qq;
+  }
+}
+// group g = threadIdx.x >> 3 is folded by its 8 lanes (fixed xor tree); valid in lane k8 == 0 of the first 256 threads
+__device__ __forceinline__ float gn_group_sum(const float* sm_a, const float* sm_k, float cnt, int cpg) {
+  const int g = threadIdx.x >> 3, k8 = threadIdx.x & 7;
+  float gs = 0.f;
+  if (g < 32)
+    for (int cc = k8; cc < cpg; cc += 8) gs += sm_a[g * cpg + cc] + cnt * sm_k[g * cpg + cc];
+  if (threadIdx.x < 256) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
+  }
+  return gs;
+}
+__device__ __forceinline__ float gn_group_m2(const float* sm_a, const float* sm_q, const float* sm_k, const float* mean,
+                                             float cnt, int cpg) {
+  const int g = threadIdx.x >> 3, k8 = threadIdx.x & 7;
+  float m2 = 0.f;
+  if (g < 32)
+    for (int cc = k8; cc < cpg; cc += 8) {
+      const int c = g * cpg + cc;
+      const float d = mean[g] - sm_k[c];
+      m2 += sm_q[c] - 2.f * d * sm_a[c] + cnt * d * d;
+    }
+  if (threadIdx.x < 256) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+  }
+  return m2;
+}
+
+// Pass 1 of the two-kernel path.  grid (splits, Nimg), block >= max(256, VT*R) threads: thread (r, vt), r < R, owns
+// channel vector vt and pixels p0+r, p0+r+R, ... of this split.  partial[n][split][2][C] = per-channel (S_c, Q_c) of the
+// split; the LAST block of an image (atomic ticket) folds the splits in index order and writes the per-(image, channel)
+// affine ab[n][c] = (gamma*rstd, beta - mean*gamma*rstd).  Deterministic: fixed per-thread pixel sequence, fixed
 // shared-memory fold, fixed split order -- no floating-point atomics; the ticket only elects who folds.
 // The split geometry depends on (HW, C) alone, so an image's statistics do not depend on the batch it is in.
 __global__ void __launch_bounds__(384) gn_stats_kernel(NormSrc s0, NormSrc s1, int HW, int cpg, int splits, int px_per,
                                                         int VT, int R, float* __restrict__ partial,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, float2* __restrict__ ab, unsigned* __restrict__ tickets) {
-  extern __shared__ float sm_gn[];  // [2][R*VT*8] per-thread channel sums, later mean/rstd
+  extern __shared__ float sm_gn[];
   __shared__ int is_last;
+  __shared__ float stat[64];  // mean[32], rstd[32]
   const int n = blockIdx.y, split = blockIdx.x;
   const int C = s0.C + s1.C;
   const int nthr = VT * R;
   float* sm_a = sm_gn;
   float* sm_q = sm_gn + nthr * 8;
+  float* sm_k = sm_gn + 2 * nthr * 8;
   const int r = threadIdx.x / VT, vt = threadIdx.x % VT;
   const int p0 = split * px_per, p1 = min(HW, p0 + px_per);
-  float a[8], q[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { a[i] = 0.f; q[i] = 0.f; }
   const bool active = threadIdx.x < nthr;
   if (active) {
     long long ps;
     const __half* base = norm_src_ptr(s0, s1, vt << 3, ps);
     base += static_cast<long long>(n) * HW * ps;
-    auto acc = [&](const uint4& u) {
-      const __half2* h = reinterpret_cast<const __half2*>(&u);
+    float a[8], q[8], k[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(h[i]);
-        a[2 * i] += f.x; q[2 * i] += f.x * f.x;
-        a[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
-      }
-    };
-    int px = p0 + r;
-    for (; px + 3 * R < p1; px += 4 * R) {
-      const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(base + px * ps));
-      const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(base + (px + R) * ps));
-      const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(base + (px + 2 * R) * ps));
-      const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(base + (px + 3 * R) * ps));
-      acc(u0); acc(u1); acc(u2); acc(u3);
-    }
-    for (; px < p1; px += R) acc(__ldg(reinterpret_cast<const uint4*>(base + px * ps)));
-  }
-  if (active) {
+    for (int i = 0; i < 8; ++i) { a[i] = 0.f; q[i] = 0.f; }
+    gn_unpack8(__ldg(reinterpret_cast<const uint4*>(base)), k);
+    gn_accumulate<4>(base, ps, p0, p1, r, R, k, a, q);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       sm_a[threadIdx.x * 8 + i] = a[i];  // index = (r*VT + vt)*8 + i = r*C + channel
       sm_q[threadIdx.x * 8 + i] = q[i];
+      if (r == 0) sm_k[vt * 8 + i] = k[i];
     }
   }
   __syncthreads();
+  gn_fold_channels(sm_a, sm_q, C, R);
+  __syncthreads();
   {
-    // group g folded by 8 consecutive lanes (k = lane & 7), then a fixed xor tree
-    const int g = threadIdx.x >> 3, k = threadIdx.x & 7;
-    float gs = 0.f, gq = 0.f;
-    if (g < 32) {
-      for (int rr = 0; rr < R; ++rr)
-        for (int cc = k; cc < cpg; cc += 8) {
-          gs += sm_a[rr * C + g * cpg + cc];
-          gq += sm_q[rr * C + g * cpg + cc];
-        }
-    }
-    if (threadIdx.x < 256) {  // whole warps (blockDim >= 256 is guaranteed by the launcher)
-#pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {
-        gs += __shfl_xor_sync(0xffffffffu, gs, o);
-        gq += __shfl_xor_sync(0xffffffffu, gq, o);
-      }
-      if (k == 0) {
-        float* o = partial + ((static_cast<long long>(n) * splits + split) * 32 + g) * 2;
-        o[0] = gs;
-        o[1] = gq;
-      }
+    float* o = partial + (static_cast<long long>(n) * splits + split) * 2 * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      o[c] = sm_a[c];
+      o[C + c] = sm_q[c];
     }
   }
   __threadfence();
@@ -110,26 +166,30 @@ __global__ void __launch_bounds__(384) gn_stats_kernel(NormSrc s0, NormSrc s1, i
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  float* mean_s = sm_gn;
-  float* rstd_s = sm_gn + 32;
-  if (threadIdx.x < 32) {
-    float s = 0.f, qq = 0.f;
-    const float* pp = partial + (static_cast<long long>(n) * splits * 32 + threadIdx.x) * 2;
-    for (int i = 0; i < splits; ++i) {
-      s += __ldcg(pp + i * 64);
-      qq += __ldcg(pp + i * 64 + 1);
+  {
+    const float* pp = partial + static_cast<long long>(n) * splits * 2 * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s = 0.f, qq = 0.f;
+      for (int i = 0; i < splits; ++i) {
+        s += __ldcg(pp + static_cast<long long>(i) * 2 * C + c);
+        qq += __ldcg(pp + static_cast<long long>(i) * 2 * C + C + c);
+      }
+      sm_a[c] = s;
+      sm_q[c] = qq;
     }
-    const float cnt = static_cast<float>(HW) * cpg;
-    const float mean = s / cnt;
-    const float var = fmaxf(qq / cnt - mean * mean, 0.f);
-    mean_s[threadIdx.x] = mean;
-    rstd_s[threadIdx.x] = rsqrtf(var + eps);
   }
+  __syncthreads();
+  const float cnt = static_cast<float>(HW);
+  const float gs = gn_group_sum(sm_a, sm_k, cnt, cpg);
+  if (threadIdx.x < 256 && (threadIdx.x & 7) == 0) stat[threadIdx.x >> 3] = gs / (cnt * cpg);
+  __syncthreads();
+  const float m2 = gn_group_m2(sm_a, sm_q, sm_k, stat, cnt, cpg);
+  if (threadIdx.x < 256 && (threadIdx.x & 7) == 0) stat[32 + (threadIdx.x >> 3)] = rsqrtf(fmaxf(m2 / (cnt * cpg), 0.f) + eps);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
-    const float sc = gamma[c] * rstd_s[g];
-    ab[static_cast<long long>(n) * C + c] = make_float2(sc, beta[c] - mean_s[g] * sc);
+    const float sc = gamma[c] * stat[32 + g];
+    ab[static_cast<long long>(n) * C + c] = make_float2(sc, beta[c] - stat[g] * sc);
   }
   if (threadIdx.x == 0) tickets[n] = 0;  // self-cleaning for the next GroupNorm on this stream
 }
@@ -182,11 +242,12 @@ __global__ void __launch_bounds__(384) gn_apply_kernel(NormSrc s0, NormSrc s1, i
 
 // Fused GroupNorm for images that fit in L2 (every U-Net activation): ONE kernel, one thread-block cluster per image.
 // grid (CL, Nimg), cluster (CL, 1, 1): CTA `rank` owns pixels [rank*px_per, (rank+1)*px_per) of image blockIdx.y.
-//   pass 1  per-thread channel sums over the CTA's pixel slice (same thread map as gn_stats_kernel), folded to 32
-//           group partials in shared memory
-//   cluster.sync, every CTA reads the CL partials of its image through distributed shared memory IN RANK ORDER
+//   pass 1  per-thread shifted channel sums over the CTA's pixel slice (same thread map as gn_stats_kernel), folded to
+//           per-channel totals and 32 group sums in shared memory
+//   cluster.sync, every CTA reads the CL group sums of its image through distributed shared memory IN RANK ORDER
 //           (deterministic: fixed slices, fixed fold, fixed order -- and the geometry depends on (HW, C) only, so an
-//           image's statistics do not depend on the batch it is in)
+//           image's statistics do not depend on the batch it is in) -> group means; a second exchange of the
+//           per-CTA sums of squared deviations about those means -> variances
 //   pass 2  the slice is read again -- an L2 hit, it was streamed a few microseconds ago -- normalised (+SiLU) and
 //           written.  HBM traffic = 1 read + 1 write of the activation (the two-kernel path reads it twice).
 __global__ void __launch_bounds__(384) gn_fused_kernel(NormSrc s0, NormSrc s1, int HW, int cpg, int px_per, int VT, int R,
@@ -194,9 +255,10 @@ __global__ void __launch_bounds__(384) gn_fused_kernel(NormSrc s0, NormSrc s1, i
                                                        float eps, int silu, __half* __restrict__ out) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
-  extern __shared__ float sm_gn[];  // [2][R*VT*8] per-thread channel sums
-  __shared__ float part[64];        // this CTA's (sum, sumsq) per group
-  __shared__ float stat[64];        // mean[32], rstd[32]
+  extern __shared__ float sm_gn[];
+  __shared__ float part[32];   // this CTA's raw sum per group
+  __shared__ float part2[32];  // this CTA's sum of squared deviations per group
+  __shared__ float stat[64];   // mean[32], rstd[32]
   const int n = blockIdx.y;
   const int rank = static_cast<int>(cluster.block_rank());
   const int CL = static_cast<int>(cluster.num_blocks());
@@ -204,82 +266,54 @@ __global__ void __launch_bounds__(384) gn_fused_kernel(NormSrc s0, NormSrc s1, i
   const int nthr = VT * R;
   float* sm_a = sm_gn;
   float* sm_q = sm_gn + nthr * 8;
+  float* sm_k = sm_gn + 2 * nthr * 8;
   const int r = threadIdx.x / VT, vt = threadIdx.x % VT;
-  const int p0 = rank * px_per, p1 = min(HW, p0 + px_per);
+  const int p0 = min(HW, rank * px_per), p1 = min(HW, p0 + px_per);
   const bool active = threadIdx.x < nthr;
   long long ps = 0;
   const __half* base = nullptr;
   if (active) {
     base = norm_src_ptr(s0, s1, vt << 3, ps);
     base += static_cast<long long>(n) * HW * ps;
-  }
-  float a[8], q[8];
+    float a[8], q[8], k[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { a[i] = 0.f; q[i] = 0.f; }
-  if (active) {
-    auto acc = [&](const uint4& u) {
-      const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(h[i]);
-        a[2 * i] += f.x; q[2 * i] += f.x * f.x;
-        a[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
-      }
-    };
-    int px = p0 + r;
-    for (; px + 7 * R < p1; px += 8 * R) {
-      uint4 u[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(base + (px + k * R) * ps));
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc(u[k]);
-    }
-    for (; px < p1; px += R) acc(__ldg(reinterpret_cast<const uint4*>(base + px * ps)));
+    for (int i = 0; i < 8; ++i) { a[i] = 0.f; q[i] = 0.f; }
+    gn_unpack8(__ldg(reinterpret_cast<const uint4*>(base)), k);
+    gn_accumulate<8>(base, ps, p0, p1, r, R, k, a, q);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       sm_a[threadIdx.x * 8 + i] = a[i];  // index = r*C + channel
       sm_q[threadIdx.x * 8 + i] = q[i];
+      if (r == 0) sm_k[vt * 8 + i] = k[i];
     }
   }
   __syncthreads();
+  gn_fold_channels(sm_a, sm_q, C, R);
+  __syncthreads();
+  const float cnt = static_cast<float>(p1 - p0);
   {
-    // group g folded by 8 consecutive lanes (k = lane & 7), then a fixed xor tree
-    const int g = threadIdx.x >> 3, k = threadIdx.x & 7;
-    float gs = 0.f, gq = 0.f;
-    if (g < 32) {
-      for (int rr = 0; rr < R; ++rr)
-        for (int cc = k; cc < cpg; cc += 8) {
-          gs += sm_a[rr * C + g * cpg + cc];
-          gq += sm_q[rr * C + g * cpg + cc];
-        }
-    }
-    if (threadIdx.x < 256) {  // whole warps (blockDim >= 256 is guaranteed by the launcher)
-#pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {
-        gs += __shfl_xor_sync(0xffffffffu, gs, o);
-        gq += __shfl_xor_sync(0xffffffffu, gq, o);
-      }
-      if (k == 0) {
-        part[2 * g] = gs;
-        part[2 * g + 1] = gq;
-      }
-    }
+    const float gs = gn_group_sum(sm_a, sm_k, cnt, cpg);
+    if (threadIdx.x < 256 && (threadIdx.x & 7) == 0) part[threadIdx.x >> 3] = gs;
+  }
+  cluster.sync();
+  const float tot = static_cast<float>(HW) * cpg;
+  if (threadIdx.x < 32) {
+    float s = 0.f;
+    for (int c = 0; c < CL; ++c) s += cluster.map_shared_rank(part, c)[threadIdx.x];
+    stat[threadIdx.x] = s / tot;
+  }
+  __syncthreads();
+  {
+    const float m2 = gn_group_m2(sm_a, sm_q, sm_k, stat, cnt, cpg);
+    if (threadIdx.x < 256 && (threadIdx.x & 7) == 0) part2[threadIdx.x >> 3] = m2;
   }
   cluster.sync();
   if (threadIdx.x < 32) {
-    float s = 0.f, qq = 0.f;
-    for (int c = 0; c < CL; ++c) {
-      const float* rp = cluster.map_shared_rank(part, c);
-      s += rp[2 * threadIdx.x];
-      qq += rp[2 * threadIdx.x + 1];
-    }
-    const float cnt = static_cast<float>(HW) * cpg;
-    const float mean = s / cnt;
-    const float var = fmaxf(qq / cnt - mean * mean, 0.f);
-    stat[threadIdx.x] = mean;
-    stat[32 + threadIdx.x] = rsqrtf(var + eps);
+    float m2 = 0.f;
+    for (int c = 0; c < CL; ++c) m2 += cluster.map_shared_rank(part2, c)[threadIdx.x];
+    stat[32 + threadIdx.x] = rsqrtf(fmaxf(m2 / tot, 0.f) + eps);
   }
-  cluster.sync();  // also keeps every CTA's `part` alive until all remote reads are done
+  cluster.sync();  // also keeps every CTA's partials alive until all remote reads are done
   if (!active) return;
   const int c = vt << 3;
   float sa[8], sb[8];

@@ -52,6 +52,18 @@ static void make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t*
   DM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
 }
 
+
+// cudaFuncSetAttribute is per device: one-time kernel configuration is keyed by the current device ordinal, so a second
+// engine on another GPU of the same process configures its own copy of every kernel
+static bool first_use_on_this_device(bool (&done)[64]) {
+  int dev = 0;
+  DM_CUDA(cudaGetDevice(&dev));
+  DM_CHECK(dev >= 0 && dev < 64, "device ordinal out of range");
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 // ------------------------------------------------------------------ kernel-variant switches
 static int g_igemm_pair = -1, g_gn_fused = -1;
 static int env_or(const char* name, int dflt) {
@@ -221,11 +233,10 @@ IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms) {
 
 template <int BN, bool DIRECT, int CG, int NG = 2>
 static void igemm_launch_bn(const IgemmOp& op, cudaStream_t s) {
-  static bool configured = false;
+  static bool configured[64] = {};
   using Cfg = IgCfg<BN, DIRECT, CG, NG>;
-  if (!configured) {
+  if (first_use_on_this_device(configured)) {
     DM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, DIRECT, CG, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
   }
   if (CG == 1) {
     igemm_kernel<BN, DIRECT, CG, NG><<<op.grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
@@ -322,33 +333,30 @@ AttnOp attn_prepare(const AttnDesc& d) {
 
 template <int D, int BKV>
 static void attn_launch_d(const AttnOp& op, cudaStream_t s) {
-  static bool configured = false;
+  static bool configured[64] = {};
   using Cfg = AttnCfg<D, BKV>;
-  if (!configured) {
+  if (first_use_on_this_device(configured)) {
     DM_CUDA(cudaFuncSetAttribute(attention_kernel<D, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
   }
   attention_kernel<D, BKV><<<op.grid, 128, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
   DM_CUDA(cudaGetLastError());
 }
 template <int D, int BKV, int ST>
 static void attn2_launch_d(const AttnOp& op, cudaStream_t s) {
-  static bool configured = false;
+  static bool configured[64] = {};
   using Cfg = Attn2Cfg<D, BKV, ST>;
-  if (!configured) {
+  if (first_use_on_this_device(configured)) {
     DM_CUDA(cudaFuncSetAttribute(attention2_kernel<D, BKV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
   }
   attention2_kernel<D, BKV, ST><<<op.grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
   DM_CUDA(cudaGetLastError());
 }
 template <int D>
 static void xattn_launch_d(const AttnOp& op, cudaStream_t s) {
-  static bool configured = false;
+  static bool configured[64] = {};
   using Cfg = XAttnCfg<D>;
-  if (!configured) {
+  if (first_use_on_this_device(configured)) {
     DM_CUDA(cudaFuncSetAttribute(xattention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
   }
   xattention_kernel<D><<<op.grid, 128, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
   DM_CUDA(cudaGetLastError());
@@ -418,18 +426,17 @@ void gn_launch(const GnDesc& d, cudaStream_t s) {
   const int cpg = C / 32;
   const GnGeom g = gn_geom(d.HW, C);
   NormSrc s0{d.src0, d.C0, d.ps0}, s1{d.src1, d.C1, d.ps1};
-  const size_t smem = static_cast<size_t>(g.VT) * g.R * 8 * 2 * sizeof(float);
+  const size_t smem = gn_smem_floats(g.VT, g.R) * sizeof(float);
   // images that fit in L2 comfortably: one fused kernel, one cluster per image (1 HBM read + 1 write)
   if (gn_use_fused(d.HW, C)) {
     // cluster size depends on HW only (batch invariance); 16 = non-portable size, allowed on sm_100
     static const int cl_max = env_or("DM_GN_CLUSTER", 8);  // 16 measured 8 % slower (r01)
     int CL = d.HW >= 2048 ? 16 : d.HW >= 512 ? 8 : d.HW >= 256 ? 4 : d.HW >= 128 ? 2 : 1;
     CL = std::min(CL, cl_max);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (first_use_on_this_device(configured)) {
       DM_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      configured = true;
-    }
+      }
     const int px_per = (d.HW + CL - 1) / CL;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(CL, d.Nimg, 1);
@@ -481,10 +488,11 @@ void layernorm_launch(const __half* x, long long ld_x, const float* gamma, const
 
 void patch3x3_launch(const float* x0, const int* x_index, const float* noise, const int* noise_index, const long long* t,
                      const float* ca, const float* cb, int Bf, int Cin, int H, int W, __half* out, cudaStream_t s,
-                     int index_stride) {
+                     int index_stride, int sched_n, int* err_flag) {
   DM_CHECK(9 * Cin <= 64, "patch3x3: Cin too large");
   patch3x3_kernel<<<grid_for(static_cast<long long>(Bf) * H * W * 8), 256, 0, s>>>(x0, x_index, noise, noise_index, t, ca,
-                                                                                   cb, Bf, Cin, H, W, index_stride, out);
+                                                                                   cb, sched_n, err_flag, Bf, Cin, H, W,
+                                                                                   index_stride, out);
   DM_CUDA(cudaGetLastError());
 }
 void repeat_rows_launch(const __half* in, long long rows, long long row_elems, int G, __half* out, cudaStream_t s) {

@@ -105,7 +105,7 @@ struct GnDesc {
   const float *gamma = nullptr, *beta = nullptr;
   float eps = 1e-5f;
   int silu = 0;
-  float* partial = nullptr;  // scratch [Nimg * splits * 64]
+  float* partial = nullptr;  // scratch [Nimg * splits * 2 * C] (two-kernel path: per-split per-channel shifted sums)
   float* ab = nullptr;       // scratch [Nimg * C * 2]: per-(image, channel) scale / shift
   unsigned* tickets = nullptr;  // scratch [Nimg], zero on entry, left zero
   __half* out = nullptr;     // dense [Nimg, HW, C0+C1]
@@ -117,7 +117,7 @@ void layernorm_launch(const __half* x, long long ld_x, const float* gamma, const
                       int C, __half* out, long long ld_out, cudaStream_t s);
 void patch3x3_launch(const float* x0, const int* x_index, const float* noise, const int* noise_index, const long long* t,
                      const float* ca, const float* cb, int Bf, int Cin, int H, int W, __half* out, cudaStream_t s,
-                     int index_stride = 1);
+                     int index_stride = 1, int sched_n = 0, int* err_flag = nullptr);
 void repeat_rows_launch(const __half* in, long long rows, long long row_elems, int G, __half* out, cudaStream_t s);
 int variant_prefix_share();  // 1 = run the (x_t, t)-only prefix of the U-Net once per draw in dm_typicality
 void timestep_embed_launch(const long long* t, const int* t_index, int Bf, __half* out, cudaStream_t s);

@@ -62,7 +62,7 @@ struct Builder {
       d.gamma = e.F(wkey + ".weight"); d.beta = e.F(wkey + ".bias");
       d.eps = eps; d.silu = silu ? 1 : 0;
       d.partial = e.gn_partial; d.ab = e.gn_ab; d.tickets = e.gn_tickets;
-      DM_CHECK(static_cast<size_t>(64) * x0.N * gn_splits(x0.N, d.HW) <= e.gn_partial_floats &&
+      DM_CHECK(static_cast<size_t>(2) * C * x0.N * gn_splits(x0.N, d.HW) <= e.gn_partial_floats &&
                    static_cast<size_t>(2) * x0.N * C <= e.gn_ab_floats && static_cast<size_t>(x0.N) <= e.gn_ticket_count,
                "GroupNorm scratch too small");
       d.out = hp(o);

@@ -198,6 +198,14 @@ class Engine:
         torch.cuda.synchronize(self.device)
         return out
 
+    def profile_plan(self, kind: str, Bf: int, h: int, w: int, aux: int = 0, iters: int = 3) -> dict:
+        """CUDA-event timing of one replay of a cached plan by op class (roofline reporting).  kind: "unet" (aux = rows per
+        shared-prefix group), "dift" (aux = up_ft_index) or "vae" (h, w = image size)."""
+        ms = (ctypes.c_double * 3)()
+        fl = (ctypes.c_double * 2)()
+        _abi.check(self.lib.dm_profile_plan(self._h, {"unet": 0, "dift": 1, "vae": 2}[kind], Bf, h, w, aux, iters, ms, fl))
+        return {"ms_igemm": ms[0], "ms_attn": ms[1], "ms_other": ms[2], "flops_igemm": fl[0], "flops_attn": fl[1]}
+
     def profile_unet(self, Bf: int, h: int, w: int, iters: int = 3) -> dict:
         v = [ctypes.c_double() for _ in range(5)]
         _abi.check(self.lib.dm_profile_unet(self._h, Bf, h, w, iters, *[ctypes.byref(x) for x in v]))

@@ -103,6 +103,12 @@ int64_t dm_debug_fetch(dm_engine* e, const char* name, float* out_dev, int64_t c
 int dm_profile_unet(dm_engine* e, int Bf, int h, int w, int iters, double* ms_igemm, double* ms_attn, double* ms_other,
                     double* flops_igemm, double* flops_attn);
 
+/* same for any cached plan: kind 0 = U-Net eps (aux = rows per shared-prefix group, 0/1 = unshared), 1 = DIFT partial
+ * forward (aux = up_ft_index), 2 = VAE encoder (h, w = image size).  ms_by_class[3] = {implicit GEMM, attention, other},
+ * flops_by_class[2] = {implicit GEMM, attention} algorithmic FLOPs of one replay. */
+int dm_profile_plan(dm_engine* e, int kind, int Bf, int h, int w, int aux, int iters, double* ms_by_class,
+                    double* flops_by_class);
+
 /* ---- T-map consumer: replaces Cluster.load_typicality + df_D + get_non_overlapping
  * (cluster.py:125-137,183-205; utils.py:74-102) for the engine's own T maps.  T: DEVICE fp32 [B,h,w] (dm_typicality
  * output, one condition); the map is resized bilinearly (align_corners=False) to H x W, average-pooled with a kx x ky

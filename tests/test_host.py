@@ -117,3 +117,65 @@ def test_exists_and_call_roundtrip():
         np.save(open(d.get_path("a/France__1.jpg"), "wb"), arr)
         assert d.exists("a/France__1.jpg")
         np.testing.assert_array_equal(d("a/France__1.jpg"), arr)
+
+
+# ---------------------------------------------------------------------------- mixed-size sharding (config 4 / geo)
+def test_shard_by_area_is_balanced_and_deterministic():
+    rng = np.random.RandomState(0)
+    areas = [int(h * w) for h, w in zip(rng.randint(24, 96, 1000), rng.randint(24, 96, 1000))]
+    shards = parallel.shard_by_area(areas, 8)
+    assert sorted(i for s in shards for i in s) == list(range(1000))
+    loads = [sum(areas[i] for i in s) for s in shards]
+    assert max(loads) - min(loads) <= max(areas)            # LPT bound
+    assert max(loads) / (sum(areas) / 8) < 1.01
+    assert shards == parallel.shard_by_area(list(areas), 8)  # no dependence on anything but the areas
+    assert parallel.shard_by_area([5, 5, 5], 1) == [[0, 1, 2]]
+    assert parallel.shard_by_area([], 4) == [[], [], [], []]
+
+
+def _shapes_mixed(n):
+    rng = np.random.RandomState(3)
+    return [(int(h), int(w)) for h, w in zip(rng.randint(2, 9, n), rng.randint(2, 9, n))]
+
+
+def _map_of(i, shape):
+    return (torch.arange(shape[0] * shape[1], dtype=torch.float32).view(shape) * 0.5 + i).contiguous()
+
+
+def _mixed_worker(rank, world, port, n_total, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shapes = _shapes_mixed(n_total)
+        out = parallel.run_sharded_mixed(shapes, lambda idx: [_map_of(i, shapes[i]) for i in idx])
+        ok = all(torch.equal(out[i], _map_of(i, shapes[i])) for i in range(n_total))
+        # async gather of equal-size maps completes on result()
+        idx = parallel.shard_indices(n_total, world, rank)
+        loc = torch.stack([torch.full((2, 3), float(i)) for i in idx]) if idx else torch.zeros(0, 2, 3)
+        h = parallel.gather_tmaps_async(loc, n_total)
+        full = h.result()
+        ok = ok and torch.equal(full, torch.stack([torch.full((2, 3), float(i)) for i in range(n_total)]))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [13, 2])
+def test_run_sharded_mixed_gloo_world2(n_total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + n_total) % 2000
+    procs = [ctx.Process(target=_mixed_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_run_sharded_mixed_single_process():
+    shapes = _shapes_mixed(9)
+    out = parallel.run_sharded_mixed(shapes, lambda idx: [_map_of(i, shapes[i]) for i in idx])
+    assert all(torch.equal(out[i], _map_of(i, shapes[i])) for i in range(9))

@@ -139,5 +139,63 @@ def layers():
     print("DMPROF_TOTAL", pr)
 
 
+def _engine(vae=False):
+    from diff_mining_b200.engine import Engine
+    from oracle import sd15
+
+    eng = Engine(0)
+    eng.load_state_dict(sd15.make_synthetic_weights(sd15.unet_param_shapes(), seed=0), "unet.")
+    if vae:
+        eng.load_state_dict(sd15.make_synthetic_weights(sd15.vae_encoder_param_shapes(), seed=1), "vae.")
+    eng.finalize()
+    g = torch.Generator().manual_seed(5)
+    for i in range(15):
+        eng.set_context(i, torch.randn(77, 768, generator=g))
+    return eng, g
+
+
+def _bracket(fn):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
+    fn()
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+
+
+def typ():
+    """ONE micro-batch of the benched config-2 plan: 54 forwards @64x64 as 27 (eps,t) draws x {c, uncond}, shared prefix"""
+    eng, g = _engine()
+    x0 = torch.randn(1, 4, 64, 64, generator=g)
+    noise = torch.randn(27, 4, 64, 64, generator=g)
+    t = torch.randint(100, 700, (27,), generator=g)
+    _bracket(lambda: eng.typicality(x0, noise, t, [1, 0], max_forwards=56))
+
+
+def typ5():
+    """ONE micro-batch of the benched config-5 plan: 15 forwards @128x128 = one (eps,t) draw x (14 conditions + uncond)"""
+    eng, g = _engine()
+    x0 = torch.randn(1, 4, 128, 128, generator=g)
+    noise = torch.randn(1, 4, 128, 128, generator=g)
+    t = torch.randint(0, 1000, (1,), generator=g)
+    _bracket(lambda: eng.typicality(x0, noise, t, list(range(1, 15)) + [0]))
+
+
+def dift():
+    """ONE micro-batch of the benched config-3 plan: 64 DIFT members @64x64, t=161, up_ft_index=1"""
+    eng, g = _engine()
+    lat = torch.randn(64, 4, 64, 64, generator=g)
+    nz = torch.randn(64, 4, 64, 64, generator=g)
+    _bracket(lambda: eng.dift(lat, nz, 161, 1, 8, up_ft_index=1))
+
+
+def vae():
+    """VAE encode of 16 images 512x512 (config 2's per-step encode)"""
+    eng, g = _engine(vae=True)
+    img = torch.rand(16, 3, 512, 512, generator=g) * 2 - 1
+    _bracket(lambda: eng.vae_encode(img, None))
+
+
 if __name__ == "__main__":
-    {"unet": unet, "ops": ops, "layers": layers, "attn": attn}[sys.argv[1]]()
+    {"unet": unet, "ops": ops, "layers": layers, "attn": attn, "typ": typ, "typ5": typ5, "dift": dift, "vae": vae}[sys.argv[1]]()
