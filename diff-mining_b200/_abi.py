@@ -23,6 +23,8 @@ SIGNATURES = {
     "dm_destroy": (I, [P]),
     "dm_load_tensor": (I, [P, ctypes.c_char_p, P, I, I, ctypes.POINTER(L)]),
     "dm_finalize_weights": (I, [P]),
+    "dm_save_packed": (I, [P, ctypes.c_char_p]),
+    "dm_load_packed": (I, [P, ctypes.c_char_p]),
     "dm_set_schedule": (I, [P, P, P, I]),
     "dm_set_context": (I, [P, I, P, P]),
     "dm_vae_encode": (I, [P, P, P, I, I, I, P, P, P, P]),

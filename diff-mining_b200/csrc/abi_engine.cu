@@ -139,6 +139,20 @@ extern "C" int dm_finalize_weights(dm_engine* h) {
     h->eng.finalize();
   });
 }
+extern "C" int dm_save_packed(dm_engine* h, const char* path) {
+  return abi_guard([&] {
+    DM_CHECK(h && path, "dm_save_packed: null argument");
+    DeviceScope dev_scope(h->eng.device);
+    h->eng.save_packed(path);
+  });
+}
+extern "C" int dm_load_packed(dm_engine* h, const char* path) {
+  return abi_guard([&] {
+    DM_CHECK(h && path, "dm_load_packed: null argument");
+    DeviceScope dev_scope(h->eng.device);
+    h->eng.load_packed(path);
+  });
+}
 extern "C" int dm_set_schedule(dm_engine* h, const float* a, const float* b, int n) {
   return abi_guard([&] {
     DM_CHECK(h, "null engine");

@@ -115,6 +115,14 @@ void Engine::load_tensor(const std::string& key, const void* host, int dtype, in
 
 namespace {
 
+void alloc_kv_cache(Engine& e, const std::string& a2, int C) {
+  __half* kv = static_cast<__half*>(e.dmalloc(static_cast<size_t>(kMaxCtxSlots) * kCtxTokens * 2 * C * sizeof(__half)));
+  DM_CUDA(cudaMemset(kv, 0, static_cast<size_t>(kMaxCtxSlots) * kCtxTokens * 2 * C * sizeof(__half)));
+  e.kv_cache[a2] = kv;
+  e.kv_C[a2] = C;
+  e.xattn_layers.push_back(a2);
+}
+
 struct Packer {
   Engine& e;
   const HostTensor& get(const std::string& k) {
@@ -129,12 +137,14 @@ struct Packer {
     __half* d = static_cast<__half*>(e.dmalloc(v.size() * sizeof(__half)));
     DM_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(__half), cudaMemcpyHostToDevice));
     e.wh[name] = d;
+    e.wh_n[name] = v.size();
     return d;
   }
   float* up_f(const std::string& name, const std::vector<float>& v) {
     float* d = static_cast<float*>(e.dmalloc(v.size() * sizeof(float)));
     DM_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
     e.wf[name] = d;
+    e.wf_n[name] = v.size();
     return d;
   }
   void vec(const std::string& k, int pad_to = 0) {
@@ -233,12 +243,7 @@ struct Packer {
     }
     mat(t + ".ff.net.2", true);
     // context K/V cache for this cross-attention layer
-    const std::string a2 = t + ".attn2";
-    __half* kv = static_cast<__half*>(e.dmalloc(static_cast<size_t>(kMaxCtxSlots) * kCtxTokens * 2 * C * sizeof(__half)));
-    DM_CUDA(cudaMemset(kv, 0, static_cast<size_t>(kMaxCtxSlots) * kCtxTokens * 2 * C * sizeof(__half)));
-    e.kv_cache[a2] = kv;
-    e.kv_C[a2] = C;
-    e.xattn_layers.push_back(a2);
+    alloc_kv_cache(e, t + ".attn2", C);
   }
 };
 
@@ -347,6 +352,10 @@ void Engine::finalize() {
     }
   }
   staging.clear();
+  finish_setup();
+}
+
+void Engine::finish_setup() {
   gn_partial_floats = 64ull * 64 * 8192;  // 64 floats x <=64 splits x <=8192 images
   gn_partial = static_cast<float*>(dmalloc(gn_partial_floats * sizeof(float)));
   gn_ab_floats = 8ull << 20;  // 2 floats x (images x channels) <= 4 Mi entries
@@ -393,6 +402,119 @@ void Engine::set_schedule(const float* a, const float* b, int n) {
   }
   DM_CUDA(cudaMemcpy(sched_a, a, n * sizeof(float), cudaMemcpyHostToDevice));
   DM_CUDA(cudaMemcpy(sched_b, b, n * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+// ------------------------------------------------------------------ packed-weight cache
+// One file holding the engine's packed device buffers exactly as finalize() leaves them (repacked conv weights, fused
+// q|k|v, interleaved GEGLU rows, stacked time_emb_proj, fp32 bias / norm vectors), so a later process skips the diffusers
+// state-dict intake and the host-side repacking.  Layout: "DMPK0002", flags, then named records.
+namespace {
+constexpr char kPackMagic[8] = {'D', 'M', 'P', 'K', '0', '0', '0', '2'};
+struct FileW {
+  FILE* f;
+  void raw(const void* p, size_t n) { DM_CHECK(fwrite(p, 1, n, f) == n, "packed-weight cache: short write"); }
+  template <class T> void pod(const T& v) { raw(&v, sizeof(T)); }
+  void str(const std::string& s) { pod<uint32_t>(static_cast<uint32_t>(s.size())); raw(s.data(), s.size()); }
+};
+struct FileR {
+  FILE* f;
+  void raw(void* p, size_t n) { DM_CHECK(fread(p, 1, n, f) == n, "packed-weight cache: truncated file"); }
+  template <class T> T pod() { T v; raw(&v, sizeof(T)); return v; }
+  std::string str() {
+    const uint32_t n = pod<uint32_t>();
+    DM_CHECK(n < 4096, "packed-weight cache: corrupt name");
+    std::string s(n, '\0');
+    raw(&s[0], n);
+    return s;
+  }
+};
+}  // namespace
+
+void Engine::save_packed(const std::string& path) const {
+  DM_CHECK(finalized, "save_packed needs finalized weights");
+  DM_CUDA(cudaSetDevice(device));
+  FILE* f = fopen(path.c_str(), "wb");
+  DM_CHECK(f != nullptr, "cannot open '" + path + "' for writing");
+  try {
+    FileW w{f};
+    w.raw(kPackMagic, 8);
+    w.pod<uint8_t>(has_unet ? 1 : 0);
+    w.pod<uint8_t>(has_vae ? 1 : 0);
+    w.pod<int32_t>(tproj_total);
+    w.pod<uint32_t>(static_cast<uint32_t>(tproj_off.size()));
+    for (auto& kv : tproj_off) { w.str(kv.first); w.pod<int32_t>(kv.second); }
+    w.pod<uint32_t>(static_cast<uint32_t>(xattn_layers.size()));
+    for (auto& a2 : xattn_layers) { w.str(a2); w.pod<int32_t>(kv_C.at(a2)); }
+    std::vector<char> host;
+    w.pod<uint32_t>(static_cast<uint32_t>(wh.size()));
+    for (auto& kv : wh) {
+      const size_t n = wh_n.at(kv.first);
+      host.resize(n * sizeof(__half));
+      DM_CUDA(cudaMemcpy(host.data(), kv.second, host.size(), cudaMemcpyDeviceToHost));
+      w.str(kv.first); w.pod<uint64_t>(n); w.raw(host.data(), host.size());
+    }
+    w.pod<uint32_t>(static_cast<uint32_t>(wf.size()));
+    for (auto& kv : wf) {
+      const size_t n = wf_n.at(kv.first);
+      host.resize(n * sizeof(float));
+      DM_CUDA(cudaMemcpy(host.data(), kv.second, host.size(), cudaMemcpyDeviceToHost));
+      w.str(kv.first); w.pod<uint64_t>(n); w.raw(host.data(), host.size());
+    }
+    w.raw(kPackMagic, 8);  // trailer: a truncated file never validates
+  } catch (...) {
+    fclose(f);
+    remove(path.c_str());
+    throw;
+  }
+  fclose(f);
+}
+
+void Engine::load_packed(const std::string& path) {
+  DM_CHECK(!finalized && staging.empty(), "load_packed needs a fresh engine");
+  DM_CUDA(cudaSetDevice(device));
+  FILE* f = fopen(path.c_str(), "rb");
+  DM_CHECK(f != nullptr, "cannot open '" + path + "'");
+  try {
+    FileR r{f};
+    char magic[8];
+    r.raw(magic, 8);
+    DM_CHECK(std::memcmp(magic, kPackMagic, 8) == 0, "'" + path + "' is not a packed-weight cache of this engine version");
+    has_unet = r.pod<uint8_t>() != 0;
+    has_vae = r.pod<uint8_t>() != 0;
+    tproj_total = r.pod<int32_t>();
+    for (uint32_t i = 0, n = r.pod<uint32_t>(); i < n; ++i) { std::string k = r.str(); tproj_off[k] = r.pod<int32_t>(); }
+    std::vector<std::pair<std::string, int>> xl;
+    for (uint32_t i = 0, n = r.pod<uint32_t>(); i < n; ++i) { std::string k = r.str(); xl.push_back({k, r.pod<int32_t>()}); }
+    std::vector<char> host;
+    for (uint32_t i = 0, n = r.pod<uint32_t>(); i < n; ++i) {
+      std::string k = r.str();
+      const uint64_t ne = r.pod<uint64_t>();
+      DM_CHECK(ne < (1ull << 32), "packed-weight cache: corrupt record");
+      host.resize(ne * sizeof(__half));
+      r.raw(host.data(), host.size());
+      __half* d = static_cast<__half*>(dmalloc(host.size()));
+      DM_CUDA(cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice));
+      wh[k] = d; wh_n[k] = ne;
+    }
+    for (uint32_t i = 0, n = r.pod<uint32_t>(); i < n; ++i) {
+      std::string k = r.str();
+      const uint64_t ne = r.pod<uint64_t>();
+      DM_CHECK(ne < (1ull << 32), "packed-weight cache: corrupt record");
+      host.resize(ne * sizeof(float));
+      r.raw(host.data(), host.size());
+      float* d = static_cast<float*>(dmalloc(host.size()));
+      DM_CUDA(cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice));
+      wf[k] = d; wf_n[k] = ne;
+    }
+    r.raw(magic, 8);
+    DM_CHECK(std::memcmp(magic, kPackMagic, 8) == 0, "'" + path + "' is truncated");
+    for (auto& x : xl) alloc_kv_cache(*this, x.first, x.second);
+  } catch (...) {
+    fclose(f);
+    throw;
+  }
+  fclose(f);
+  finish_setup();
 }
 
 void Engine::set_context(int slot, const float* ctx, cudaStream_t s) {

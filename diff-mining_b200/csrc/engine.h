@@ -93,6 +93,7 @@ struct Engine {
   // packed device parameters
   std::map<std::string, __half*> wh;  // fp16 matrices [N, K]
   std::map<std::string, float*> wf;   // fp32 vectors
+  std::map<std::string, size_t> wh_n, wf_n;  // element counts of the packed buffers (packed-weight cache)
   std::map<std::string, int> tproj_off;  // resnet name -> column offset in the stacked time_emb_proj output
   int tproj_total = 0;
   std::vector<void*> owned;           // every cudaMalloc to free
@@ -129,6 +130,9 @@ struct Engine {
 
   void load_tensor(const std::string& key, const void* host, int dtype, int ndim, const int64_t* shape);
   void finalize();
+  void finish_setup();                       // scratch, default schedule, capture stream (after packing or load_packed)
+  void save_packed(const std::string& path) const;  // packed device buffers -> one file
+  void load_packed(const std::string& path);        // replaces load_tensor... + finalize
   void set_schedule(const float* a, const float* b, int n);
   void set_context(int slot, const float* ctx, cudaStream_t s);
 

@@ -72,7 +72,8 @@ static int env_or(const char* name, int dflt) {
 }
 static int variant_igemm_pair() { return g_igemm_pair >= 0 ? g_igemm_pair : env_or("DM_IGEMM_PAIR", 1); }
 static int variant_gn_fused() { return g_gn_fused >= 0 ? g_gn_fused : env_or("DM_GN_FUSED", 1); }
-static int g_xattn = -1, g_prefix = -1, g_ng4 = -1;
+static int g_xattn = -1, g_prefix = -1, g_ng4 = -1, g_attn3 = -1;
+static int variant_attn3() { return g_attn3 >= 0 ? g_attn3 : env_or("DM_ATTN3", 1); }
 static int variant_igemm_ng4() { return g_ng4 >= 0 ? g_ng4 : env_or("DM_IGEMM_NG4", 1); }
 int variant_prefix_share() { return g_prefix >= 0 ? g_prefix : env_or("DM_PREFIX_SHARE", 1); }
 static int variant_xattn() { return g_xattn >= 0 ? g_xattn : env_or("DM_XATTN", 1); }
@@ -82,6 +83,7 @@ void set_variant(const std::string& name, int value) {
   else if (name == "xattn") g_xattn = value;
   else if (name == "prefix_share") g_prefix = value;
   else if (name == "igemm_ng4") g_ng4 = value;
+  else if (name == "attn3") g_attn3 = value;
   else DM_CHECK(false, "unknown kernel variant '" + name + "'");
 }
 
@@ -326,7 +328,16 @@ AttnOp attn_prepare(const AttnDesc& d) {
   op.p.kv_index = d.kv_index;
   op.p.out = d.out; op.p.ld_out = d.ld_out;
   op.p.scale_log2 = static_cast<float>(1.0 / std::sqrt(static_cast<double>(d.D)) * 1.4426950408889634);
-  op.grid = op.v2 ? dim3((d.Tq + 255) / 256, d.heads, d.B) : dim3((d.Tq + 127) / 128, d.heads, d.B);
+  op.v3 = (op.v2 && variant_attn3()) ? 1 : 0;
+  if (op.v3) {
+    int dev = 0, sms = 0;
+    DM_CUDA(cudaGetDevice(&dev));
+    DM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long work = static_cast<long long>((d.Tq + 255) / 256) * d.heads * d.B;
+    op.grid = dim3(static_cast<unsigned>(std::min<long long>(work, sms)), 1, 1);  // persistent CTAs
+  } else {
+    op.grid = op.v2 ? dim3((d.Tq + 255) / 256, d.heads, d.B) : dim3((d.Tq + 127) / 128, d.heads, d.B);
+  }
   op.flops = 4.0 * d.B * d.heads * static_cast<double>(d.Tq) * d.Tk * d.D;
   return op;
 }
@@ -351,6 +362,19 @@ static void attn2_launch_d(const AttnOp& op, cudaStream_t s) {
   attention2_kernel<D, BKV, ST><<<op.grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
   DM_CUDA(cudaGetLastError());
 }
+template <int D, int BKV, int ST, int VAR>
+static void attn3_launch_d(const AttnOp& op, cudaStream_t s) {
+  static bool configured[64] = {};
+  using Cfg = Attn3Cfg<D, BKV, ST>;
+  if (first_use_on_this_device(configured)) {
+    DM_CUDA(cudaFuncSetAttribute(attention3_kernel<D, BKV, ST, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  }
+  attention3_kernel<D, BKV, ST, VAR><<<op.grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
+  DM_CUDA(cudaGetLastError());
+}
+#ifndef DM_ATTN3_VAR
+#define DM_ATTN3_VAR 0
+#endif
 template <int D>
 static void xattn_launch_d(const AttnOp& op, cudaStream_t s) {
   static bool configured[64] = {};
@@ -369,6 +393,36 @@ void attn_launch(const AttnOp& op, cudaStream_t s) {
       case 160: xattn_launch_d<160>(op, s); break;
       default: DM_CHECK(false, "attention: unsupported head_dim");
     }
+    return;
+  }
+  if (op.v3) {
+#ifdef DM_ATTN3_EXPERIMENT
+    // tuning build: attn3 = 1 + VAR selects the variant at run time (tools/ab.py attn)
+    const int var = variant_attn3() - 1;
+    if (op.D == 40) {
+      switch (var) {
+        case 1: attn3_launch_d<40, 128, 2, 1>(op, s); break;
+        case 2: attn3_launch_d<40, 128, 2, 2>(op, s); break;
+        case 4: attn3_launch_d<40, 128, 2, 4>(op, s); break;
+        case 5: attn3_launch_d<40, 128, 2, 5>(op, s); break;
+        case 8: attn3_launch_d<40, 128, 2, 8>(op, s); break;
+        case 12: attn3_launch_d<40, 128, 2, 12>(op, s); break;
+        case 13: attn3_launch_d<40, 128, 2, 13>(op, s); break;
+        case 14: attn3_launch_d<40, 128, 2, 14>(op, s); break;
+        default: attn3_launch_d<40, 128, 2, 0>(op, s); break;
+      }
+    } else {
+      switch (var) {
+        case 13: attn3_launch_d<80, 64, 3, 13>(op, s); break;
+        case 12: attn3_launch_d<80, 64, 3, 12>(op, s); break;
+        case 14: attn3_launch_d<80, 64, 3, 14>(op, s); break;
+        default: attn3_launch_d<80, 64, 3, 0>(op, s); break;
+      }
+    }
+    return;
+#endif
+    if (op.D == 40) attn3_launch_d<40, 128, 2, DM_ATTN3_VAR>(op, s);
+    else attn3_launch_d<80, 64, 3, DM_ATTN3_VAR>(op, s);
     return;
   }
   if (op.v2) {

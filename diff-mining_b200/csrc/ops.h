@@ -8,7 +8,7 @@
 #include <stdexcept>
 #include <string>
 
-#include "attention2.cuh"
+#include "attention3.cuh"
 #include "igemm.cuh"
 
 namespace dm {
@@ -90,6 +90,7 @@ struct AttnOp {
   AttnParams p;
   int D = 0;
   int v2 = 0;     // 1 = warp-specialised two-Q-tile kernel (attention2.cuh)
+  int v3 = 0;     // 1 = its persistent successor (attention3.cuh): grid = min(#work items, #SMs)
   int xattn = 0;  // 1 = short-key-set kernel (<= 80 keys, P in tensor memory)
   dim3 grid;
   double flops = 0;

@@ -69,6 +69,33 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t p
     }
   }
 }
+// Relaxed wait for the single-thread helper roles (TMA producer, MMA issuers, ...): the polling thread shares its SM
+// sub-partition's issue port with the math warps, so every failed probe suspends in hardware for up to `hint_ns`
+// (mbarrier.try_wait's suspend-time hint) instead of spinning through the instruction stream.
+static __device__ __noinline__ void mbar_wait_relaxed_slow(uint32_t bar_addr, uint32_t parity) {
+  const long long t0 = clock64();
+  for (int it = 0;; ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) return;
+    if ((it & 63) == 63 && clock64() - t0 > DM_WAIT_LIMIT_CYCLES) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_relaxed_slow(smem_u32(bar), parity);
+}
+__device__ __forceinline__ void tma_prefetch_l2_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   if (mbar_try_wait(bar, parity)) return;

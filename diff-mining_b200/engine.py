@@ -3,6 +3,7 @@ host<->device copies; every FLOP of the hot path runs in libdm_b200.so."""
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
@@ -26,6 +27,70 @@ def _dev_f32(t: torch.Tensor, device) -> torch.Tensor:
     return t.to(device=device, dtype=torch.float32).contiguous()
 
 
+class ContextSlots:
+    """The engine's ONE allocator of text-context slots (its cross-attention K/V caches hold MAX_CTX_SLOTS contexts).
+
+    Contexts are keyed by CONTENT (hash of the fp32 [77,768] values), so the same prompt embedding always maps to the same
+    slot no matter which object (typicality.SD, dift.SDFeaturizer) or tensor storage it arrives through.  `acquire` takes
+    every context one engine call needs and returns their slots; slots holding one of those contexts are pinned for the call,
+    the least recently used other slot is recycled for each context that is not resident, and a call that needs more distinct
+    contexts than there are slots raises.  Uploads (16 small K/V GEMMs per context) are stream-ordered with the call that
+    follows.  Slots written through Engine.set_context() directly are "manual": the allocator never recycles them."""
+
+    def __init__(self, engine: "Engine", n_slots: int = MAX_CTX_SLOTS):
+        self.engine = engine
+        self.n = n_slots
+        self.key_of: List[Optional[bytes]] = [None] * n_slots
+        self.manual = [False] * n_slots
+        self.last_use = [0] * n_slots
+        self.slot_of: Dict[bytes, int] = {}
+        self.tick = 0
+        self.uploads = 0
+
+    @staticmethod
+    def key(ctx: torch.Tensor) -> bytes:
+        import hashlib
+
+        a = ctx.detach().to(device="cpu", dtype=torch.float32).contiguous()
+        if tuple(a.shape) != (77, 768):
+            raise ValueError(f"context must be [77, 768], got {tuple(a.shape)}")
+        return hashlib.blake2b(a.numpy().tobytes(), digest_size=16).digest()
+
+    def mark_manual(self, slot: int) -> None:
+        k = self.key_of[slot]
+        if k is not None:
+            self.slot_of.pop(k, None)
+        self.key_of[slot] = None
+        self.manual[slot] = True
+
+    def acquire(self, ctxs: Sequence[torch.Tensor]) -> List[int]:
+        keys = [self.key(c) for c in ctxs]
+        need = {}
+        for k, c in zip(keys, ctxs):
+            need.setdefault(k, c)
+        free = [s for s in range(self.n) if not self.manual[s]]
+        if len(need) > len(free):
+            raise RuntimeError(f"one call needs {len(need)} distinct text contexts but the engine has {len(free)} context slots "
+                               f"({self.n} total, {self.n - len(free)} set manually)")
+        self.tick += 1
+        for k in need:
+            if k in self.slot_of:
+                self.last_use[self.slot_of[k]] = self.tick
+        for k, c in need.items():
+            if k in self.slot_of:
+                continue
+            # victim: an unused slot first, else the least recently used slot that this call does not need
+            cand = [s for s in free if self.key_of[s] is None or self.key_of[s] not in need]
+            s = min(cand, key=lambda i: (self.key_of[i] is not None, self.last_use[i], i))
+            old = self.key_of[s]
+            if old is not None:
+                del self.slot_of[old]
+            self.engine._upload_context(s, c)
+            self.uploads += 1
+            self.key_of[s], self.slot_of[k], self.last_use[s] = k, s, self.tick
+        return [self.slot_of[k] for k in keys]
+
+
 class Engine:
     """One engine per (process, GPU).  Not re-entrant; all work is enqueued on torch's current stream."""
 
@@ -38,6 +103,7 @@ class Engine:
         _abi.check(self.lib.dm_create(self.device.index or 0, ctypes.byref(h)))
         self._h = h
         self._finalized = False
+        self.contexts = ContextSlots(self)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -88,12 +154,26 @@ class Engine:
         _abi.check(self.lib.dm_finalize_weights(self._h))
         self._finalized = True
 
+    def save_packed(self, path: str) -> None:
+        """packed-weight cache: the engine's packed device buffers -> one file"""
+        _abi.check(self.lib.dm_save_packed(self._h, os.fsencode(path)))
+
+    def load_packed(self, path: str) -> None:
+        """fresh engine <- packed-weight cache (replaces load_state_dict + finalize)"""
+        _abi.check(self.lib.dm_load_packed(self._h, os.fsencode(path)))
+        self._finalized = True
+
     def set_schedule(self, sqrt_acp: torch.Tensor, sqrt_1m_acp: torch.Tensor) -> None:
         a = sqrt_acp.detach().float().cpu().contiguous()
         b = sqrt_1m_acp.detach().float().cpu().contiguous()
         _abi.check(self.lib.dm_set_schedule(self._h, _ptr(a), _ptr(b), a.numel()))
 
     def set_context(self, slot: int, ctx: torch.Tensor) -> None:
+        """write a context into an explicit slot (low-level use: tests, bench); the slot leaves the allocator's pool"""
+        self._upload_context(slot, ctx)
+        self.contexts.mark_manual(int(slot))
+
+    def _upload_context(self, slot: int, ctx: torch.Tensor) -> None:
         c = ctx.detach().float().cpu().contiguous()
         if tuple(c.shape) != (77, 768):
             raise ValueError(f"context must be [77, 768], got {tuple(c.shape)}")

@@ -23,7 +23,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 
-from .engine import Engine, MAX_CTX_SLOTS
+from .engine import Engine
 
 VAE_SCALING = 0.18215
 
@@ -46,25 +46,137 @@ def prompt_for(which: str, c: str) -> str:
     return f"{c}" if len(c) else ""
 
 
-def load_diffusers_dir(model_path: str) -> Dict[str, Dict[str, torch.Tensor]]:
-    """Read `unet/` and `vae/` safetensors of a diffusers pipeline directory (the on-disk contract the
-    reference's fine-tuning export produces, finetuning/base.py:245-259)."""
-    from safetensors.torch import load_file
+# AutoencoderKL attention blocks saved before diffusers 0.15 (the stock runwayml/stable-diffusion-v1-5 and
+# CompVis/stable-diffusion-v1-4 VAE checkpoints among them) use these names; diffusers renames them when loading
+# (AutoencoderKL / Attention `_convert_deprecated_attention_blocks`), so the reference never sees them -- we do.
+_DEPRECATED_VAE_ATTN = {"query": "to_q", "key": "to_k", "value": "to_v", "proj_attn": "to_out.0"}
 
+
+def normalize_vae_keys(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """keep `encoder.*` / `quant_conv.*`, map the deprecated attention names (query/key/value/proj_attn ->
+    to_q/to_k/to_v/to_out.0) and squeeze attention weights that were stored as 1x1 convolutions ([C,C,1,1] -> [C,C])"""
     out = {}
-    for sub in ("unet", "vae"):
-        p = join(model_path, sub, "diffusion_pytorch_model.safetensors")
-        if not os.path.isfile(p):
-            p16 = join(model_path, sub, "diffusion_pytorch_model.fp16.safetensors")
-            if os.path.isfile(p16):
-                p = p16
-            else:
-                raise FileNotFoundError(f"{p} not found (need a diffusers SD-1.5 directory)")
-        sd = load_file(p)
-        if sub == "vae":
-            sd = {k: v for k, v in sd.items() if k.startswith("encoder.") or k.startswith("quant_conv.")}
-        out[sub] = sd
+    for k, v in sd.items():
+        if not (k.startswith("encoder.") or k.startswith("quant_conv.")):
+            continue
+        parts = k.split(".")
+        if "attentions" in parts:
+            for old, new in _DEPRECATED_VAE_ATTN.items():
+                if parts[-2] == old:
+                    k = ".".join(parts[:-2] + new.split(".") + parts[-1:])
+                    break
+            if k.endswith(".weight") and v.dim() == 4 and v.shape[2:] == (1, 1) and ".attentions." in k and "group_norm" not in k:
+                v = v[:, :, 0, 0]
+        out[k] = v
     return out
+
+
+def resolve_model_path(model_path: str) -> str:
+    """A local diffusers pipeline directory, or a hub id (the reference's defaults 'runwayml/stable-diffusion-v1-5' /
+    'CompVis/stable-diffusion-v1-4', compute.py:60-66,383) resolved through the LOCAL Hugging Face cache -- this engine
+    never downloads."""
+    if os.path.isdir(model_path):
+        return model_path
+    try:
+        from huggingface_hub import snapshot_download
+
+        return snapshot_download(model_path, local_files_only=True, allow_patterns=["model_index.json", "unet/*", "vae/*", "scheduler/*"])
+    except Exception as ex:  # noqa: BLE001
+        raise FileNotFoundError(f"'{model_path}' is neither a diffusers pipeline directory nor a hub id present in the local "
+                                f"Hugging Face cache ({type(ex).__name__}: {ex})") from ex
+
+
+def _load_weights_file(folder: str) -> Dict[str, torch.Tensor]:
+    """diffusers weight files in its own preference order: safetensors (fp32, then the .fp16. variant), then torch .bin"""
+    names = ["diffusion_pytorch_model.safetensors", "diffusion_pytorch_model.fp16.safetensors", "diffusion_pytorch_model.bin",
+             "diffusion_pytorch_model.fp16.bin"]
+    for n in names:
+        p = join(folder, n)
+        if os.path.isfile(p):
+            if n.endswith(".safetensors"):
+                from safetensors.torch import load_file
+
+                return load_file(p)
+            return torch.load(p, map_location="cpu", weights_only=True)
+    raise FileNotFoundError(f"no diffusion_pytorch_model.(fp16.)safetensors/.bin under {folder} (need a diffusers SD-1.5 directory)")
+
+
+def weight_files(model_path: str) -> List[str]:
+    """the files load_diffusers_dir would read (for cache keys)"""
+    root = resolve_model_path(model_path)
+    out = []
+    for sub in ("unet", "vae"):
+        for n in ("diffusion_pytorch_model.safetensors", "diffusion_pytorch_model.fp16.safetensors", "diffusion_pytorch_model.bin",
+                  "diffusion_pytorch_model.fp16.bin"):
+            if os.path.isfile(join(root, sub, n)):
+                out.append(join(root, sub, n))
+                break
+    return out
+
+
+def load_diffusers_dir(model_path: str) -> Dict[str, Dict[str, torch.Tensor]]:
+    """Read `unet/` and `vae/` of a diffusers pipeline directory -- the on-disk contract of the reference: the fine-tuning
+    export writes it (finetuning/base.py:245-259) and compute.py:383-385 probes `model_index.json` to recognise one --
+    or of a hub id in the local cache.  Returns {"unet": state dict, "vae": encoder + quant_conv state dict} in the
+    current diffusers key schema."""
+    root = resolve_model_path(model_path)
+    if not os.path.isfile(join(root, "model_index.json")) and not os.path.isdir(join(root, "unet")):
+        raise FileNotFoundError(f"{root} is not a diffusers pipeline directory (no model_index.json / unet/)")
+    return {"unet": _load_weights_file(join(root, "unet")), "vae": normalize_vae_keys(_load_weights_file(join(root, "vae")))}
+
+
+def packed_cache_path(model_path: str, cache_dir: Optional[str] = None) -> str:
+    """File name of the packed-weight cache of a checkpoint: keyed by a hash over, for every weight file the loader would
+    read, its size, mtime and first / last MiB (hashing 4 GB of fp32 weights in full would cost more than the load it
+    saves).  Directory: `cache_dir`, else $DM_WEIGHT_CACHE, else ~/.cache/dm_b200."""
+    import hashlib
+
+    h = hashlib.blake2b(digest_size=16)
+    h.update(b"dm_b200 packed weights v2")
+    for f in weight_files(model_path):
+        st = os.stat(f)
+        h.update(f"{os.path.basename(os.path.dirname(f))}/{os.path.basename(f)}:{st.st_size}:{st.st_mtime_ns}".encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read(1 << 20))
+            if st.st_size > (2 << 20):
+                fh.seek(st.st_size - (1 << 20))
+                h.update(fh.read(1 << 20))
+    d = cache_dir or os.environ.get("DM_WEIGHT_CACHE") or os.path.join(os.path.expanduser("~"), ".cache", "dm_b200")
+    return os.path.join(d, f"sd15_{h.hexdigest()}.dmpk")
+
+
+def load_engine_weights(engine: Engine, model_path: Optional[str], state_dicts=None, *, cache: bool = True,
+                        cache_dir: Optional[str] = None) -> str:
+    """Fill a fresh engine: explicit `state_dicts` ({"unet": ..., "vae": ...}, diffusers keys), else the packed-weight
+    cache of `model_path` when one exists, else the diffusers directory / hub id itself (writing the cache afterwards).
+    Returns which source was used: "state_dicts" | "packed_cache" | "diffusers"."""
+    if state_dicts is not None:
+        for name in ("unet", "vae"):
+            if name in state_dicts:
+                engine.load_state_dict(state_dicts[name], name + ".")
+        engine.finalize()
+        return "state_dicts"
+    cpath = packed_cache_path(model_path, cache_dir) if cache else None
+    if cpath and os.path.isfile(cpath):
+        try:
+            engine.load_packed(cpath)
+            return "packed_cache"
+        except RuntimeError:
+            os.remove(cpath)  # stale / truncated: fall through to the checkpoint (load_packed leaves nothing half-loaded
+            raise             # only on a fresh engine, so surface the error rather than continue on this one)
+    sds = load_diffusers_dir(model_path)
+    engine.load_state_dict(sds["unet"], "unet.")
+    engine.load_state_dict(sds["vae"], "vae.")
+    engine.finalize()
+    if cpath:
+        try:
+            os.makedirs(os.path.dirname(cpath), exist_ok=True)
+            tmp = cpath + f".tmp{os.getpid()}"
+            engine.save_packed(tmp)
+            os.replace(tmp, cpath)
+        except (OSError, RuntimeError):
+            pass  # a read-only cache directory must not fail the run
+    return "diffusers"
 
 
 class SD(object):
@@ -76,12 +188,7 @@ class SD(object):
         self.which = which
         self.device = torch.device(device)
         self.engine = Engine(self.device)
-        sds = state_dicts if state_dicts is not None else load_diffusers_dir(model_path)
-        if "unet" in sds:
-            self.engine.load_state_dict(sds["unet"], "unet.")
-        if "vae" in sds:
-            self.engine.load_state_dict(sds["vae"], "vae.")
-        self.engine.finalize()
+        self.weights_source = load_engine_weights(self.engine, model_path, state_dicts)
         a, b = scaled_linear_schedule()
         self.engine.set_schedule(a, b)
         self.scheduler = SimpleNamespace(num_train_timesteps=1000)
@@ -97,37 +204,22 @@ class SD(object):
                 text_encoder = ClipTextEncoder(clip_name, self.device)
             cf = text_encoder([prompt_for(which, c) for c in apply_categories])
             category_embeds = {c: cf[i] for i, c in enumerate(apply_categories)}
+        # every category embedding stays on the device (the reference keeps the same dict, compute.py:78-79); engine context
+        # slots are handed out per call by the engine's content-keyed LRU allocator, so category counts beyond the 64
+        # slots (365 places, every country of geo) are fine: D.compute only ever needs the category and "" together
         self.country_embeds = {c: category_embeds[c].to(self.device).float() for c in apply_categories}
-        # context slots: one per known category; extra slots serve ad-hoc contexts handed to compute_loss
-        self._slot_ctx = torch.zeros(MAX_CTX_SLOTS, 77, 768, device=self.device)
-        self._slot_used = 0
-        self._slot_of: Dict[str, int] = {}
-        for c in apply_categories:
-            self._slot_of[c] = self._upload_context(self.country_embeds[c])
 
-    # ---- context slot management
-    def _upload_context(self, ctx: torch.Tensor) -> int:
-        if self._slot_used >= MAX_CTX_SLOTS:
-            self._slot_used = len(self._slot_of)  # recycle the ad-hoc slots
-        s = self._slot_used
-        self._slot_used += 1
-        self.engine.set_context(s, ctx)
-        self._slot_ctx[s] = ctx.to(self.device).float()
-        return s
-
+    # ---- context slot management (engine.ContextSlots)
     def slot(self, category: str) -> int:
-        return self._slot_of[category]
+        return self.engine.contexts.acquire([self.country_embeds[category]])[0]
 
     def slots_for(self, c: torch.Tensor) -> List[int]:
-        """Map rows of an arbitrary [M,77,768] context tensor to engine slots (uploading unseen rows)."""
+        """Map rows of an arbitrary [M,77,768] context tensor to engine slots (uploading rows that are not resident).
+        All rows of one call are pinned together; more distinct rows than slots raises."""
         c = c.to(self.device).float()
         uniq, inv = torch.unique(c.reshape(c.shape[0], -1), dim=0, return_inverse=True)
-        slot_of_uniq = []
-        for u in uniq:
-            u = u.view(77, 768)
-            hit = (self._slot_ctx[: self._slot_used] == u).flatten(1).all(dim=1).nonzero()
-            slot_of_uniq.append(int(hit[0]) if hit.numel() else self._upload_context(u))
-        return [slot_of_uniq[i] for i in inv.tolist()]
+        slots = self.engine.contexts.acquire([u.view(77, 768) for u in uniq])
+        return [slots[i] for i in inv.tolist()]
 
     # ---- reference surface
     def encode_vae(self, x):
@@ -152,9 +244,95 @@ class SD(object):
         return loss
 
 
+class AsyncNpyWriter:
+    """Per-image `.npy` output off the critical path.  The reference blocks on `.cpu()` after every
+    micro-batch and on `np.save` after every image (compute.py:156,192).  Here the raw grid of image i is copied
+    device -> pinned host on a side stream (ordered after the compute stream by an event) into one of `depth` pinned
+    buffers, and a background thread waits for that copy and writes the file -- both overlap the U-Net forwards of image
+    i+1.  The bytes written are exactly `np.save(open(path, "wb"), grid.cpu().numpy())`."""
+
+    def __init__(self, device, depth: int = 2):
+        import queue
+        import threading
+
+        self.device = torch.device(device)
+        self.depth = depth
+        self._bufs: List[Optional[torch.Tensor]] = [None] * depth
+        self._busy = [threading.Event() for _ in range(depth)]
+        for e in self._busy:
+            e.set()  # set = free
+        self._next = 0
+        self._q: "queue.Queue" = queue.Queue()
+        self._err: List[BaseException] = []
+        self._stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            path, view, ev, slot = item
+            try:
+                if ev is not None:
+                    ev.synchronize()
+                os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+                with open(path, "wb") as f:
+                    np.save(f, view.numpy())
+            except BaseException as ex:  # noqa: BLE001 -- surfaced by flush()
+                self._err.append(ex)
+            finally:
+                self._busy[slot].set()
+                self._q.task_done()
+
+    def submit(self, path: str, grid: torch.Tensor) -> None:
+        """enqueue `np.save(path, grid)`; returns as soon as the D2H copy is enqueued (blocks only while all `depth` pinned
+        buffers are still being written out)"""
+        slot = self._next
+        self._next = (self._next + 1) % self.depth
+        self._busy[slot].wait()
+        self._busy[slot].clear()
+        n = grid.numel()
+        buf = self._bufs[slot]
+        if buf is None or buf.numel() < n or buf.dtype != grid.dtype:
+            buf = torch.empty(n, dtype=grid.dtype)
+            if self._stream is not None:
+                buf = buf.pin_memory()
+            self._bufs[slot] = buf
+        view = buf[:n].view(grid.shape)
+        ev = None
+        if grid.is_cuda:
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self._stream):
+                self._stream.wait_event(done)
+                view.copy_(grid, non_blocking=True)
+                grid.record_stream(self._stream)
+                ev = torch.cuda.Event()
+                ev.record(self._stream)
+        else:
+            view.copy_(grid)
+        self._q.put((path, view, ev, slot))
+
+    def flush(self) -> None:
+        self._q.join()
+        if self._err:
+            raise self._err.pop(0)
+
+    def close(self) -> None:
+        self.flush()
+        self._q.put(None)
+        self._thread.join(timeout=10)
+
+
 class D(object):
-    def __init__(self, sd, typicality_path, which, seed=42, N=100, t_min=0.0, t_max=1.0):
+    def __init__(self, sd, typicality_path, which, seed=42, N=100, t_min=0.0, t_max=1.0, *, async_write=False):
+        """`async_write=True`: compute() hands the finished grid to an AsyncNpyWriter (pinned double-buffered D2H +
+        background np.save) so image i's write overlaps image i+1's forwards; call flush() before reading files back."""
         self.typicality_path = typicality_path
+        self.async_write = async_write
+        self._writer = None
         self.sd = sd
         self.seed = seed
         self.N = N
@@ -191,12 +369,16 @@ class D(object):
         `B` (the reference's memory knob: samples per micro-batch) is accepted for signature parity; the engine
         picks its own balanced micro-batches -- the grid is bit-identical for every batch size
         (tests/test_gpu_e2e.py::test_typicality_grid_and_T)."""
+        return self.compute_losses_device(img, country_embeds).cpu()
+
+    @torch.no_grad()
+    def compute_losses_device(self, img, country_embeds):
+        """compute_losses without the device->host copy: fp16 [N, n_cond, 4, h, w] on the engine's device"""
         x = self.sd.encode_vae(self.load_image(img))
         noises, timesteps = self.draws(x)
         slots = self.sd.slots_for(country_embeds)
-        n_cond = len(slots)
         grid, _ = self.sd.engine.typicality(x, noises, timesteps, slots, want_grid=True, want_T=False)
-        return grid[0].cpu()
+        return grid[0]
 
     @torch.no_grad()
     def compute_losses_loop(self, img, country_embeds, B=10):
@@ -248,8 +430,19 @@ class D(object):
         country_embeds = torch.stack([self.sd.country_embeds[country], self.sd.country_embeds[""]], dim=0)
         out = self.get_path(path)
         os.makedirs(os.path.dirname(out), exist_ok=True)
+        if self.async_write:
+            if self._writer is None:
+                self._writer = AsyncNpyWriter(self.sd.device)
+            self._writer.submit(out, self.compute_losses_device(img, country_embeds))
+            return
         losses = self.compute_losses(img, country_embeds)
-        np.save(open(out, "wb"), losses.numpy())
+        with open(out, "wb") as f:
+            np.save(f, losses.numpy())
+
+    def flush(self):
+        """wait until every file handed to the asynchronous writer is on disk"""
+        if self._writer is not None:
+            self._writer.flush()
 
     def __call__(self, path):
         return np.load(self.get_path(path))

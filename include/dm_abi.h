@@ -38,6 +38,12 @@ int dm_destroy(dm_engine* e);
 int dm_load_tensor(dm_engine* e, const char* key, const void* host_ptr, int dtype, int ndim, const int64_t* shape);
 int dm_finalize_weights(dm_engine* e); /* checks that every SD-1.5 tensor arrived; packs; frees staging */
 
+/* Packed-weight cache: dm_save_packed writes the packed device buffers of a finalized engine to one
+ * file; dm_load_packed on a FRESH engine replaces the whole dm_load_tensor... + dm_finalize_weights sequence (the host
+ * keys the file by a hash of the checkpoint it came from: diff-mining_b200/typicality.py packed_cache_path). */
+int dm_save_packed(dm_engine* e, const char* path);
+int dm_load_packed(dm_engine* e, const char* path);
+
 /* alphas_cumprod-derived tables of scheduler.add_noise (compute.py:99; dift.py:190): 1000 fp32 each, HOST. */
 int dm_set_schedule(dm_engine* e, const float* sqrt_acp, const float* sqrt_one_minus_acp, int n);
 
@@ -141,6 +147,7 @@ int dm_op_layernorm(const void* x, int64_t rows, int C, const float* gamma, cons
  *   igemm_ng4   1 = four epilogue warpgroups for short-K (epilogue-bound) layers, 0 = always two, 2 = wherever possible
  *   gn_fused    1 = cluster-fused single-pass GroupNorm for images that fit in L2, 0 = two-kernel path
  *   xattn       1 = short-key-set cross-attention kernel (P in tensor memory), 0 = generic flash kernel
+ *   attn3       1 = persistent self-attention kernel (attention3.cuh), 0 = one CTA per 256-query block (attention2.cuh)
  *   prefix_share 1 = dm_typicality computes the context-free U-Net prefix once per (eps,t) draw (bit-identical) */
 int dm_op_set_variant(const char* name, int value);
 

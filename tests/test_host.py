@@ -179,3 +179,52 @@ def test_run_sharded_mixed_single_process():
     shapes = _shapes_mixed(9)
     out = parallel.run_sharded_mixed(shapes, lambda idx: [_map_of(i, shapes[i]) for i in idx])
     assert all(torch.equal(out[i], _map_of(i, shapes[i])) for i in range(9))
+
+
+# ---------------------------------------------------------------------------- context-slot allocator
+class _FakeEngine:
+    def __init__(self):
+        self.uploaded = []
+
+    def _upload_context(self, slot, ctx):
+        self.uploaded.append((slot, float(ctx[0, 0])))
+
+
+def _ctx(i):
+    return torch.full((77, 768), float(i))
+
+
+def test_context_slots_lru_pinning_and_overflow():
+    from diff_mining_b200.engine import ContextSlots
+
+    fe = _FakeEngine()
+    cs = ContextSlots(fe, n_slots=4)
+    assert cs.acquire([_ctx(1), _ctx(2), _ctx(1)]) == [0, 1, 0]          # content-keyed: equal values share a slot
+    assert cs.acquire([_ctx(2).clone()]) == [1] and len(fe.uploaded) == 2  # other storage, same content: no upload
+    assert cs.acquire([_ctx(3), _ctx(4)]) == [2, 3]
+    # all four slots hold 1..4; a call needing {5, 2} must keep 2 and recycle the least recently used of the others (1)
+    assert cs.acquire([_ctx(5), _ctx(2)]) == [0, 1]
+    assert cs.slot_of[ContextSlots.key(_ctx(3))] == 2 and ContextSlots.key(_ctx(1)) not in cs.slot_of
+    # one call may never evict a context it needs itself: 4 new contexts replace everything, 5 is too many
+    assert sorted(cs.acquire([_ctx(i) for i in (10, 11, 12, 13)])) == [0, 1, 2, 3]
+    with pytest.raises(RuntimeError, match="distinct text contexts"):
+        cs.acquire([_ctx(i) for i in range(20, 25)])
+    # manual slots leave the pool
+    cs.mark_manual(0)
+    got = cs.acquire([_ctx(30), _ctx(31), _ctx(32)])
+    assert 0 not in got and len(set(got)) == 3
+    with pytest.raises(RuntimeError):
+        cs.acquire([_ctx(i) for i in range(40, 44)])
+
+
+def test_context_slots_many_categories():
+    """the reference builds SD with every category (365 for places): a (category, "") pair per call must always fit"""
+    from diff_mining_b200.engine import ContextSlots
+
+    fe = _FakeEngine()
+    cs = ContextSlots(fe, n_slots=64)
+    uncond = _ctx(0)
+    for c in range(1, 366):
+        s = cs.acquire([_ctx(c), uncond])
+        assert s[0] != s[1]
+    assert len(fe.uploaded) == 366   # the unconditional context stayed resident the whole time (most recently used)

@@ -1,0 +1,87 @@
+"""A/B timing + correctness of kernel variants through the op-level C ABI (development aid, run under gpurun).
+   python tools/ab.py attn      self-attention shapes of the U-Net, every value of the `attn3` switch
+   python tools/ab.py gn        GroupNorm shapes, fused vs two-kernel
+Times: CUDA events on the launching stream, median of `reps` launches after warm-up; inputs are larger than L2 at the
+big shapes."""
+import ctypes
+import os
+import statistics
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import gpu_optest as o  # noqa: E402
+
+lib, ptr, stream = o.lib, o.ptr, o.stream
+lib.dm_op_set_variant.argtypes = [ctypes.c_char_p, ctypes.c_int]
+
+
+def timeit(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts), min(ts)
+
+
+def attn():
+    shapes = [(54, 4096, 40), (27, 4096, 40), (54, 1024, 80), (15, 16384, 40), (15, 4096, 80), (3, 1000, 40), (2, 300, 80), (1, 4096, 40)]
+    variants = [int(v) for v in os.environ.get("AB_VARIANTS", "0,1").split(",")]
+    if os.environ.get("AB_SHAPES"):
+        shapes = [tuple(int(x) for x in sh.split("x")) for sh in os.environ["AB_SHAPES"].split(",")]
+    for (B, T, D) in shapes:
+        C = 8 * D
+        g = torch.Generator(device="cuda").manual_seed(B + T + D)
+        qkv = (torch.randn(B, T, 3 * C, device="cuda", generator=g) * 1.5).half()
+        out = torch.empty(B, T, C, device="cuda", dtype=torch.float16)
+        args = (ptr(qkv[..., :C]), ptr(qkv[..., C:2 * C]), ptr(qkv[..., 2 * C:]), 3 * C, 3 * C, 3 * C, T * 3 * C, T * 3 * C, T * 3 * C, B, 8, D, T, T, 0,
+                None, ptr(out), C, stream())
+        nb = min(B, 2)
+        q, k, v = [qkv[:nb, :, i * C:(i + 1) * C].float().view(nb, T, 8, D).transpose(1, 2) for i in range(3)]
+        ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(nb, T, C)
+        flops = 4.0 * B * 8 * T * T * D
+        for v_ in variants:
+            o.check(lib.dm_op_set_variant(b"attn3", v_))
+            out.zero_()
+            o.check(lib.dm_op_attention(*args))
+            torch.cuda.synchronize()
+            err = (out[:nb].float() - ref).abs().max().item() / ref.abs().max().item()
+            full_ok = bool(torch.isfinite(out.float()).all())
+            med, mn = timeit(lambda: o.check(lib.dm_op_attention(*args)))
+            print(f"ATTN B={B:3d} T={T:5d} D={D:3d} attn3={v_}: {med:8.4f} ms (min {mn:8.4f})  {flops / med / 1e9:7.1f} TFLOP/s  "
+                  f"max-rel-err {err:.2e} finite={full_ok}", flush=True)
+        o.check(lib.dm_op_set_variant(b"attn3", -1))
+
+
+def gn():
+    shapes = [(54, 4096, 320), (54, 4096, 640), (54, 4096, 960), (54, 1024, 640), (54, 1024, 1280), (54, 256, 1280), (54, 64, 2560)]
+    for (N, HW, C) in shapes:
+        x = torch.randn(N, HW, C, device="cuda").half()
+        gm = torch.randn(C, device="cuda")
+        bt = torch.randn(C, device="cuda")
+        out = torch.empty_like(x)
+        ref = F.silu(F.group_norm(x[:2].float().permute(0, 2, 1), 32, gm, bt, 1e-5)).permute(0, 2, 1)
+        for mode in (1, 0):
+            o.check(lib.dm_op_set_variant(b"gn_fused", mode))
+            f = lambda: o.check(lib.dm_op_groupnorm(ptr(x), None, N, HW, C, 0, ptr(gm), ptr(bt), 1e-5, 1, ptr(out), stream()))  # noqa: E731
+            f()
+            torch.cuda.synchronize()
+            err = (out[:2].float() - ref).abs().max().item() / ref.abs().max().item()
+            med, mn = timeit(f)
+            gbs = 2.0 * x.numel() * 2 / med / 1e6
+            print(f"GN N={N} HW={HW} C={C} fused={mode}: {med:8.4f} ms (min {mn:.4f})  {gbs:7.1f} GB/s algorithmic  err {err:.2e}", flush=True)
+        o.check(lib.dm_op_set_variant(b"gn_fused", -1))
+
+
+if __name__ == "__main__":
+    {"attn": attn, "gn": gn}[sys.argv[1]]()
