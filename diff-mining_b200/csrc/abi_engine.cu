@@ -66,7 +66,7 @@ __half* ensure_grid(dm_engine* h, size_t n) {
 // context slot ctx_idx[b] (all index arrays on the DEVICE).
 Plan* unet_microbatch(Engine& e, int kind, int aux, const float* x, const int* x_index, const float* noise,
                       const int* noise_index, const long long* t, const int* t_index, const int* ctx_idx, int Bf, int h,
-                      int w, cudaStream_t s) {
+                      int w, cudaStream_t s, __half* fused_grid = nullptr) {
   Plan* p = e.get_plan(PlanKey{kind, Bf, h, w, aux});
   // kPlanUnet with aux = G > 1: the input patch matrix is built once per group of G forwards sharing (x_t, t)
   const int G = (kind == kPlanUnet && aux > 1) ? aux : 1;
@@ -74,6 +74,11 @@ Plan* unet_microbatch(Engine& e, int kind, int aux, const float* x, const int* x
                   e.err_dev);
   timestep_embed_launch(t, t_index, Bf, p->temb_sin, s);
   DM_CUDA(cudaMemcpyAsync(p->ctx_idx, ctx_idx, Bf * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  if (kind == kPlanUnet && p->loss_args) {
+    // conv_out's fused typicality epilogue: grid rows of this micro-batch start at `fused_grid` (null = epilogue off)
+    const IgLossArgs la{noise, noise_index, nullptr, fused_grid};
+    DM_CUDA(cudaMemcpyAsync(p->loss_args, &la, sizeof(la), cudaMemcpyHostToDevice, s));
+  }
   e.launch_count += 2;
   e.run_plan(p, s);
   if (kind == kPlanUnet) e.last_unet_plan = p;
@@ -288,11 +293,9 @@ extern "C" int dm_typicality(dm_engine* h, const float* x0, const float* noise, 
       const int nb = static_cast<int>(std::min<long long>(Bf, F - f0));
       // the n_cond forwards of one (eps, t) draw are consecutive rows: share their context-free prefix
       const int share = (n_cond > 1 && variant_prefix_share()) ? n_cond : 0;
-      Plan* p = unet_microbatch(e, kPlanUnet, share, x0, dev + f0, noise, dev + F + f0, reinterpret_cast<const long long*>(t),
-                                dev + F + f0, dev + 2 * F + f0, nb, hh, ww, s);
-      loss_launch(p->out, 16, noise, dev + F + f0, nullptr, nullptr, grid + static_cast<size_t>(f0) * 4 * HW, nullptr, nb, HW,
-                  s);
-      e.launch_count += 1;
+      // (pred - eps)^2 -> fp16 grid rows [f0, f0 + nb) is formed by conv_out's epilogue: no separate loss pass
+      unet_microbatch(e, kPlanUnet, share, x0, dev + f0, noise, dev + F + f0, reinterpret_cast<const long long*>(t), dev + F + f0,
+                      dev + 2 * F + f0, nb, hh, ww, s, grid + static_cast<size_t>(f0) * 4 * HW);
     }
     if (T_out) {
       tmap_launch(grid, Bi, N, n_cond, HW, T_out, s);

@@ -355,4 +355,184 @@ __global__ void __launch_bounds__(128) xattention_kernel(const __grid_constant__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Single-head, 512-wide attention of the VAE encoder's mid block (AutoencoderKL Attention: heads = 1, dim 512,
+// /root/reference/diffmining/typicality/compute.py:91-93 reaches it through vae.encode), flash style so that no T x T
+// score matrix ever exists and any token count works (the reference encodes arbitrary image sizes).
+// The fp32 accumulator of a 128 x 512 output tile alone would fill all 512 TMEM columns, so a query tile is served by
+// TWO CTAs (blockIdx.y = which 256 output channels): each stages the full 512-wide Q tile, walks the keys in tiles of
+// 32, forms S = Q K^T (32 TMEM columns, 32 MMAs of K = 16), turns it into P in shared memory exactly like
+// attention_kernel, and accumulates its half O[:, 256 h : 256 (h+1)] += P V[:, half] (256 TMEM columns).  QK^T is computed
+// twice per query tile (1.5x the FLOPs of the op); the op is < 4 % of an encode.
+struct VAttnCfg {
+  static constexpr int DQ = 512, DV = 256, BKV = 32;
+  static constexpr int NCHQ = DQ / 64, NCHV = DV / 64;
+  static constexpr int Q_BYTES = NCHQ * 128 * 128;        // 128 KB
+  static constexpr int K_BYTES = NCHQ * BKV * 128;        // 32 KB
+  static constexpr int V_BYTES = NCHV * BKV * 128;        // 16 KB
+  static constexpr int P_BYTES = 128 * 128;               // 128-byte swizzled rows, 64 of them used per row
+  static constexpr int SMEM_BYTES = Q_BYTES + K_BYTES + V_BYTES + P_BYTES + 1024 + 128;
+  static constexpr int O_COL = BKV;
+  static constexpr int TMEM_COLS = 512;
+};
+
+template <int NSPLIT>  // CTAs per query tile (= 512 / VAttnCfg::DV); a template so the header can be included from several TUs
+__global__ void __launch_bounds__(128, 1) vattention_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
+  using Cfg = VAttnCfg;
+  static_assert(NSPLIT * Cfg::DV == Cfg::DQ, "output split");
+  constexpr int BKV = Cfg::BKV, DV = Cfg::DV;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::Q_BYTES;
+  uint8_t* sV = sK + Cfg::K_BYTES;
+  uint8_t* sP = sV + Cfg::V_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t *bar_q = bars, *bar_k = bars + 1, *bar_v = bars + 2, *bar_s = bars + 3, *bar_o = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * 128, half = blockIdx.y, b = blockIdx.z;
+  const int nkv = (p.Tk + BKV - 1) / BKV;
+
+  if (tid == 0) {
+    mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&maps.q); tma_prefetch_desc(&maps.k); tma_prefetch_desc(&maps.v);
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+
+  auto load_k = [&](int j) {
+    mbar_arrive_expect_tx(bar_k, Cfg::K_BYTES);
+    for (int c = 0; c < Cfg::NCHQ; ++c) tma_load_4d(sK + c * BKV * 128, &maps.k, bar_k, c * 64, 0, j * BKV, b);
+  };
+  auto load_v = [&](int j) {
+    mbar_arrive_expect_tx(bar_v, Cfg::V_BYTES);
+    for (int c = 0; c < Cfg::NCHV; ++c) tma_load_4d(sV + c * BKV * 128, &maps.v, bar_v, half * DV + c * 64, 0, j * BKV, b);
+  };
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, Cfg::Q_BYTES);
+    for (int c = 0; c < Cfg::NCHQ; ++c) tma_load_4d(sQ + c * 16384, &maps.q, bar_q, c * 64, 0, q0, b);
+    load_k(0);
+    load_v(0);
+    mbar_wait(bar_q, 0);
+  }
+
+  float m_run = -INFINITY, l_run = 0.f;
+  constexpr uint32_t idesc_s = umma_idesc_f16(BKV, false);
+  constexpr uint32_t idesc_o = umma_idesc_f16(DV, true);
+
+  for (int j = 0; j < nkv; ++j) {
+    const uint32_t ph = j & 1;
+    if (tid == 0) {
+      mbar_wait(bar_k, ph);
+      tc_fence_after();
+#pragma unroll 8
+      for (int ks = 0; ks < Cfg::DQ / 16; ++ks) {
+        const uint64_t ad = umma_desc_kmajor_sw128(smem_u32(sQ + (ks >> 2) * 16384)) + 2 * (ks & 3);
+        const uint64_t bd = umma_desc_kmajor_sw128(smem_u32(sK + (ks >> 2) * BKV * 128)) + 2 * (ks & 3);
+        umma_f16(tmem_base, ad, bd, idesc_s, ks != 0 ? 1u : 0u);
+      }
+      umma_commit(bar_s);
+    }
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+    if (tid == 0 && j + 1 < nkv) load_k(j + 1);  // K tile is free again: prefetch the next one under the softmax
+    const int kbase = j * BKV;
+    const bool need_mask = kbase + BKV > p.Tk;
+    uint32_t raw[BKV];
+    tmem_ld_x32(t_row, raw);
+    tmem_wait_ld();
+    float mx = m_run;
+#pragma unroll
+    for (int i = 0; i < BKV; ++i) {
+      if (need_mask && kbase + i >= p.Tk) raw[i] = 0xff800000u;
+      mx = fmaxf(mx, __uint_as_float(raw[i]));
+    }
+    const float alpha = exp2f((m_run - mx) * p.scale_log2);
+    const float moff = mx * p.scale_log2;
+    // previous PV must be done before P (its A operand) is overwritten / O is rescaled
+    if (j > 0) {
+      mbar_wait(bar_o, (j - 1) & 1);
+      tc_fence_after();
+      if (tid == 0) load_v(j);  // V tile free: fetch this iteration's tile
+    }
+    float lsum = 0.f;
+    uint32_t pk[BKV / 2];
+#pragma unroll
+    for (int i = 0; i < BKV; i += 2) {
+      const float e0 = fast_exp2(__uint_as_float(raw[i]) * p.scale_log2 - moff);
+      const float e1 = fast_exp2(__uint_as_float(raw[i + 1]) * p.scale_log2 - moff);
+      lsum += e0 + e1;
+      pk[i >> 1] = pack_h2(e0, e1);
+    }
+#pragma unroll
+    for (int i = 0; i < BKV / 8; ++i)
+      *reinterpret_cast<uint4*>(sP + tid * 128 + ((i ^ (tid & 7)) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    l_run = l_run * alpha + lsum;
+    m_run = mx;
+    if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.f)) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < DV; c0 += 16) {
+        uint32_t o[16];
+        tmem_ld_x16(t_row + Cfg::O_COL + c0, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st_x16(t_row + Cfg::O_COL + c0, o);
+      }
+      tmem_wait_st();
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(bar_v, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < BKV / 16; ++ks) {
+        const uint64_t ad = umma_desc_kmajor_sw128(smem_u32(sP)) + 2 * ks;
+        const uint64_t bd = umma_desc_mnmajor_sw128(smem_u32(sV + ks * 2048), BKV * 128);
+        umma_f16(tmem_base + Cfg::O_COL, ad, bd, idesc_o, (j | ks) != 0 ? 1u : 0u);
+      }
+      umma_commit(bar_o);
+    }
+  }
+  mbar_wait(bar_o, (nkv - 1) & 1);
+  tc_fence_after();
+  const int q = q0 + tid;
+  const float inv = 1.f / l_run;
+  __half* orow = p.out + (static_cast<long long>(b) * p.Tq + q) * p.ld_out + half * DV;
+#pragma unroll 1
+  for (int c0 = 0; c0 < DV; c0 += 16) {
+    uint32_t o[16];
+    tmem_ld_x16(t_row + Cfg::O_COL + c0, o);
+    tmem_wait_ld();
+    if (q < p.Tq) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 8)
+        *reinterpret_cast<uint4*>(orow + c0 + i) =
+            make_uint4(pack_h2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv),
+                       pack_h2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv),
+                       pack_h2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv),
+                       pack_h2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
 }  // namespace dm

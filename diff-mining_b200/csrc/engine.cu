@@ -327,20 +327,19 @@ void Engine::finalize() {
     pk.resnet(V + "mid_block.resnets.1", 512, 512, false);
     const std::string a = V + "mid_block.attentions.0";
     pk.norm(a + ".group_norm");
-    {  // fused q | k projection
+    {  // fused q | k | v projection (weights [3*512, 512], biases [3*512])
       std::vector<__half> v;
       std::vector<float> b;
-      for (const char* n : {".to_q", ".to_k"}) {
+      for (const char* n : {".to_q", ".to_k", ".to_v"}) {
         const HostTensor& w = pk.get(a + n + ".weight");
         const HostTensor& bb = pk.get(a + n + ".bias");
         pk.expect(w, a + n, {512, 512});
         v.insert(v.end(), w.data.begin(), w.data.end());
         for (auto h : bb.data) b.push_back(__half2float(h));
       }
-      pk.up_h(a + ".qk.weight", v);
-      pk.up_f(a + ".qk.bias", b);
+      pk.up_h(a + ".qkv.weight", v);
+      pk.up_f(a + ".qkv.bias", b);
     }
-    pk.mat(a + ".to_v", true);
     pk.mat(a + ".to_out.0", true);
     pk.norm(V + "conv_norm_out");
     pk.conv3(V + "conv_out", 16);

@@ -73,6 +73,7 @@ struct Plan {
   __half* a_in = nullptr;      // [B*h*w, 64] patch matrix of the input conv
   __half* temb_sin = nullptr;  // [B, 320]
   int* ctx_idx = nullptr;      // [B] context slot per row
+  IgLossArgs* loss_args = nullptr;  // U-Net plans: conv_out's fused typicality epilogue (rewritten before every replay)
   __half* out = nullptr;       // U-Net: pred [B*h*w, 16]; DIFT: feature map NHWC; VAE: conv_out [B*h*w, 16]
   int out_H = 0, out_W = 0, out_C = 0;
   std::map<std::string, Act> taps;  // debug_keep only

@@ -45,6 +45,16 @@ struct alignas(64) IgMaps {
   CUtensorMap r;  // residual [Nimg, H, W, ld_res], same box
 };
 
+// Typicality epilogue of conv_out (reference: F.mse_loss(noise_pred.float(), noise, 'none') at
+// /root/reference/diffmining/typicality/compute.py:101, stored as fp16 [.., 4, h, w] rows, compute.py:155-160): lives in
+// DEVICE memory because the pointers change per micro-batch while the prepared launch (and its CUDA graph) does not.
+struct IgLossArgs {
+  const float* noise;      // [*, 4, H, W] fp32 draws
+  const int* noise_index;  // [Nimg] forward row -> draw
+  const int* grid_row;     // [Nimg] forward row -> row of the raw grid, or null (identity offset 0)
+  __half* grid_f16;        // [rows, 4, H, W] fp16; null = epilogue disabled for this replay
+};
+
 struct IgParams {
   int Nimg, H, W;                 // OUTPUT pixel grid; M = Nimg*H*W
   int wt_log, ht_log, nt_log;     // M-tile = 2^nt images x 2^ht rows x 2^wt cols (=128 pixels)
@@ -61,6 +71,7 @@ struct IgParams {
   void* out;                      // [M, ld_out] fp16 (or fp32 when out_f32)
   long long ld_out;
   int out_f32, geglu, act_silu;
+  const IgLossArgs* loss;         // direct epilogue only: fused (pred - eps)^2 -> fp16 grid (null = off)
 };
 
 // CG = CTAs per tile: 1, or 2 = a CTA pair (cta_group::2) computing a 256 x BN tile with each CTA holding its 128
@@ -295,6 +306,20 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) igemm_kernel(const __grid_co
           }
 #pragma unroll
           for (int i = 0; i < CH; ++i) v[i] = round_h(v[i]);
+          if (p.loss != nullptr && col0 == 0) {
+            // conv_out of the typicality path: loss = (float(fp16 pred) - eps)^2 straight into the raw fp16 grid; threads of a
+            // warp hold consecutive pixels, so every channel plane is written with coalesced 2-byte stores
+            const IgLossArgs la = *p.loss;
+            if (la.grid_f16 != nullptr) {
+              const long long HW = static_cast<long long>(p.H) * p.W, px = static_cast<long long>(y) * p.W + x;
+              const long long nrow = la.noise_index ? la.noise_index[n] : n, grow = la.grid_row ? la.grid_row[n] : n;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float dlt = v[c] - __ldg(la.noise + (nrow * 4 + c) * HW + px);
+                la.grid_f16[(grow * 4 + c) * HW + px] = __float2half_rn(dlt * dlt);
+              }
+            }
+          }
           if (p.rowbias) {
             const __half* rb = p.rowbias + static_cast<long long>(n) * p.ld_rowbias + col0;
 #pragma unroll

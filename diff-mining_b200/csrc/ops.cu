@@ -176,6 +176,7 @@ IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms) {
   p.residual = d.residual; p.ld_res = d.ld_res;
   p.out = d.out; p.ld_out = d.ld_out;
   p.out_f32 = d.out_f32; p.geglu = d.geglu; p.act_silu = d.act_silu;
+  p.loss = d.loss;
   DM_CHECK(d.out != nullptr && d.ld_out % 8 == 0, "igemm: bad output");
   // staged epilogue (TMA store / residual prefetch) unless the output is fp32 or the N-tile is narrower than a chunk
   op.direct = (d.out_f32 || op.bn < 32) ? 1 : 0;
@@ -187,6 +188,7 @@ IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms) {
             (d.cg == 0 && p.m_tiles >= 2 && kit >= 16 &&  // short-K layers are epilogue-bound: pairs only couple them
              static_cast<long long>((p.m_tiles + 1) / 2) * p.n_tiles >= num_sms / 2)))
               ? 2 : 1;
+  DM_CHECK(d.loss == nullptr || (op.direct && !d.out_f32 && d.N >= 4), "igemm: the fused loss epilogue needs the direct fp16 epilogue");
   DM_CHECK(!d.geglu || (op.bn % 64 == 0 && !op.direct), "igemm: GEGLU needs an N-tile that is a multiple of 64");
   DM_CHECK(!d.geglu || (!d.residual && !d.rowbias && !d.act_silu), "igemm: GEGLU excludes the other epilogue options");
   if (!op.direct) {
@@ -303,16 +305,18 @@ void igemm_launch(const IgemmOp& op, cudaStream_t s) {
 // ------------------------------------------------------------------ attention
 AttnOp attn_prepare(const AttnDesc& d) {
   AttnOp op{};
-  DM_CHECK(d.D == 40 || d.D == 80 || d.D == 160, "attention: head_dim must be 40, 80 or 160");
+  DM_CHECK(d.D == 40 || d.D == 80 || d.D == 160 || (d.D == 512 && d.heads == 1),
+           "attention: head_dim must be 40, 80 or 160 (or one 512-wide head: the VAE mid block)");
+  op.vattn = d.D == 512 ? 1 : 0;
   DM_CHECK(d.Tq > 0 && d.Tk > 0 && d.B > 0, "attention: empty problem");
   op.D = d.D;
   // long self-attention (head_dim 40 / 80) -> warp-specialised kernel; short key sets (cross-attention, 77 keys)
   // and head_dim 160 stay on the one-tile kernel.  DM_ATTN2=0 disables, DM_ATTN2=2 also routes cross-attention.
   static const int attn2_mode = [] { const char* e = getenv("DM_ATTN2"); return e ? atoi(e) : 1; }();
-  op.v2 = (d.D == 40 || d.D == 80) && attn2_mode > 0 && (d.Tk > 128 || attn2_mode > 1) ? 1 : 0;
+  op.v2 = !op.vattn && (d.D == 40 || d.D == 80) && attn2_mode > 0 && (d.Tk > 128 || attn2_mode > 1) ? 1 : 0;
   // short key sets (text cross-attention, <= 80 keys): single-tile kernel with P kept in tensor memory
-  op.xattn = (!op.v2 && d.Tk <= 80 && variant_xattn()) ? 1 : 0;
-  const int bkv = op.xattn ? 80 : d.D == 40 ? 128 : 64;
+  op.xattn = (!op.vattn && !op.v2 && d.Tk <= 80 && variant_xattn()) ? 1 : 0;
+  const int bkv = op.vattn ? VAttnCfg::BKV : op.xattn ? 80 : d.D == 40 ? 128 : 64;
   auto mk = [&](CUtensorMap* m, const __half* ptr, long long ld, long long bs, int T, int nb, int rows) {
     const uint64_t dims[4] = {static_cast<uint64_t>(d.D), static_cast<uint64_t>(d.heads), static_cast<uint64_t>(T),
                               static_cast<uint64_t>(nb)};
@@ -329,7 +333,10 @@ AttnOp attn_prepare(const AttnDesc& d) {
   op.p.out = d.out; op.p.ld_out = d.ld_out;
   op.p.scale_log2 = static_cast<float>(1.0 / std::sqrt(static_cast<double>(d.D)) * 1.4426950408889634);
   op.v3 = (op.v2 && variant_attn3()) ? 1 : 0;
-  if (op.v3) {
+  if (op.vattn) {
+    DM_CHECK(d.kv_index == nullptr, "attention: the 512-wide kernel takes no K/V indirection");
+    op.grid = dim3((d.Tq + 127) / 128, 2, d.B);
+  } else if (op.v3) {
     int dev = 0, sms = 0;
     DM_CUDA(cudaGetDevice(&dev));
     DM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -385,7 +392,19 @@ static void xattn_launch_d(const AttnOp& op, cudaStream_t s) {
   xattention_kernel<D><<<op.grid, 128, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
   DM_CUDA(cudaGetLastError());
 }
+static void vattn_launch(const AttnOp& op, cudaStream_t s) {
+  static bool configured[64] = {};
+  if (first_use_on_this_device(configured)) {
+    DM_CUDA(cudaFuncSetAttribute(vattention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, VAttnCfg::SMEM_BYTES));
+  }
+  vattention_kernel<2><<<op.grid, 128, VAttnCfg::SMEM_BYTES, s>>>(op.maps, op.p);
+  DM_CUDA(cudaGetLastError());
+}
 void attn_launch(const AttnOp& op, cudaStream_t s) {
+  if (op.vattn) {
+    vattn_launch(op, s);
+    return;
+  }
   if (op.xattn) {
     switch (op.D) {
       case 40: xattn_launch_d<40>(op, s); break;

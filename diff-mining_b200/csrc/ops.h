@@ -53,6 +53,7 @@ struct IgemmDesc {
   void* out = nullptr;
   long long ld_out = 0;
   int out_f32 = 0, geglu = 0, act_silu = 0;
+  const IgLossArgs* loss = nullptr;  // device-resident typicality epilogue arguments (conv_out, direct epilogue only)
   int bn = 0;  // 0 = choose
   int cg = 0;  // CTAs per tile: 0 = choose, 1 = single CTA, 2 = CTA pair (cta_group::2)
 };
@@ -92,6 +93,7 @@ struct AttnOp {
   int v2 = 0;     // 1 = warp-specialised two-Q-tile kernel (attention2.cuh)
   int v3 = 0;     // 1 = its persistent successor (attention3.cuh): grid = min(#work items, #SMs)
   int xattn = 0;  // 1 = short-key-set kernel (<= 80 keys, P in tensor memory)
+  int vattn = 0;  // 1 = single-head 512-wide kernel of the VAE mid block (two CTAs per query tile)
   dim3 grid;
   double flops = 0;
 };

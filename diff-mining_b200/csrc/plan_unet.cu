@@ -189,6 +189,8 @@ void build_unet_plan(Engine& e, Plan& p, bool dry, ArenaPlanner& ar) {
   p.a_in = b.at<__half>(off_ain);
   p.temb_sin = b.at<__half>(off_sin);
   p.ctx_idx = b.at<int>(off_ctx);
+  const size_t off_loss = b.alloc_bytes(sizeof(IgLossArgs));  // zero-initialised with the arena: epilogue off
+  p.loss_args = b.at<IgLossArgs>(off_loss);
 
   // ---- time embedding: sinusoid -> Linear+SiLU -> Linear(+SiLU for the ResNets) -> all 22 time_emb_proj at once
   Act sin_a; sin_a.off = off_sin; sin_a.N = 1; sin_a.H = 1; sin_a.W = Bf; sin_a.C = 320; sin_a.valid = true;
@@ -290,7 +292,22 @@ void build_unet_plan(Engine& e, Plan& p, bool dry, ArenaPlanner& ar) {
   // ---- out: GN + SiLU -> conv 320 -> 4 (weights zero-padded to 16 rows)
   Act n = b.groupnorm("conv_norm_out", x, nullptr, U + "conv_norm_out", 1e-5f, true);
   b.release(x);
-  Act pred = b.conv3x3("conv_out", n, nullptr, U + "conv_out", 16, nullptr, 0, nullptr);
+  // conv 320 -> 4 (rows zero-padded to 16); its epilogue also forms (pred - eps)^2 into the raw fp16 grid when the
+  // call is dm_typicality (the eps-MSE "fused into the final store" of the north star)
+  Act pred = b.alloc(n.N, n.H, n.W, 16);
+  {
+    IgemmDesc d;
+    d.Nimg = n.N; d.H = n.H; d.W = n.W;
+    d.nsrc = 1;
+    d.src[0] = b.view(n);
+    seg_conv3x3(d, n.C, n.C);
+    d.Wt = dry ? nullptr : e.H(U + "conv_out.weight");
+    d.N = 16; d.K = 9 * n.C;
+    d.bias = dry ? nullptr : e.F(U + "conv_out.bias");
+    d.out = b.hp(pred); d.ld_out = 16;
+    d.loss = p.loss_args;
+    b.add_igemm("conv_out", d);
+  }
   b.release(n);
   b.tap("conv_out", pred);
   p.out = b.hp(pred);

@@ -1,7 +1,7 @@
 // Execution plan of the SD-1.5 VAE encoder (AutoencoderKL.encode up to the posterior moments), reached from
 // SD.encode_vae (/root/reference/diffmining/typicality/compute.py:91-93) and OneStepSDPipeline (dift.py:187).
-// Same kernel family as the U-Net at C = 128/256/512; the single 512-d attention head of the mid block is run
-// unfused (S = QK^T in fp32 -> row softmax -> PV) through the implicit-GEMM kernel, one image at a time.
+// Same kernel family as the U-Net at C = 128/256/512; the single 512-wide attention head of the mid block runs on its own
+// flash kernel (attention.cuh: vattention_kernel), batched over images, for any token count.
 #include "plan_builder.h"
 
 namespace dm {
@@ -55,67 +55,25 @@ struct VaeBuilder : Builder {
     return o;
   }
 
-  // Attention(heads=1, dim 512, GroupNorm, q/k/v/out with bias, residual) over T = H*W tokens per image
+  // Attention(heads=1, dim 512, GroupNorm, q/k/v/out with bias, residual) over T = H*W tokens per image: one fused
+  // q|k|v projection, the single-head flash kernel (vattention_kernel: no T x T buffer, any T, all images in one launch),
+  // output projection + residual
   Act mid_attention(const std::string& key, const Act& x) {
     const int C = x.C, T = x.H * x.W, B = x.N;
-    DM_CHECK(T % 8 == 0, "VAE attention needs (H/8)*(W/8) to be a multiple of 8; got " + std::to_string(T));
     Act n = groupnorm(key + ".group_norm", x, nullptr, key + ".group_norm", 1e-6f, false);
-    Act qk = linear(key + ".qk", n, nullptr, key + ".qk", 2 * C, true, nullptr);  // [M, q | k]
-    Act vT = alloc(B, 1, C, T);     // per image [C, T] = V^T without bias (bias re-added after PV: softmax rows sum to 1)
-    Act o = alloc(B, x.H, x.W, C);  // attention output tokens
-    const size_t s_off = alloc_bytes(static_cast<size_t>(T) * T * sizeof(float));
-    const size_t p_off = alloc_bytes(static_cast<size_t>(T) * T * sizeof(__half));
-    const int kchunks = (T + 63) / 64;
-    for (int b = 0; b < B; ++b) {
-      const __half* nb = hp(n) + static_cast<size_t>(b) * T * C;
-      const __half* qb = hp(qk) + static_cast<size_t>(b) * T * 2 * C;
-      {  // V^T[c, t] = sum_i Wv[c, i] * n[t, i]   (A = Wv as a 512-row "activation", B = tokens)
-        IgemmDesc d;
-        d.Nimg = 1; d.H = 1; d.W = C;
-        d.nsrc = 1;
-        d.src[0] = ActView{dry ? nullptr : e.H(key + ".to_v.weight"), 1, 1, C, C, C};
-        seg_1x1(d, C, 0);
-        d.Wt = nb; d.N = T; d.K = C;
-        d.out = hp(vT) + static_cast<size_t>(b) * C * T; d.ld_out = T;
-        add_igemm(key + ".vT", d);
-      }
-      {  // S = q k^T  (fp32)
-        IgemmDesc d;
-        d.Nimg = 1; d.H = 1; d.W = T;
-        d.nsrc = 1;
-        d.src[0] = ActView{qb, 1, 1, T, C, 2 * C};
-        seg_1x1(d, C, 0);
-        d.Wt = qb + C; d.N = T; d.K = C;
-        d.w_ld = 2 * C;
-        d.out = at<float>(s_off); d.ld_out = T; d.out_f32 = 1;
-        add_igemm(key + ".qk^T", d);
-      }
-      if (!dry) {
-        const float* S = at<float>(s_off);
-        __half* P = at<__half>(p_off);
-        const float scale = 1.0f / sqrtf(static_cast<float>(C));
-        push(Step{[=](cudaStream_t s) { softmax_rows_launch(S, T, T, T, scale, P, T, s); }, kStepOther, 0, 1,
-                  key + ".softmax"});
-      }
-      {  // O = P V + b_v
-        IgemmDesc d;
-        d.Nimg = 1; d.H = 1; d.W = T;
-        d.nsrc = 1;
-        d.src[0] = ActView{at<__half>(p_off), 1, 1, T, T, T};
-        d.nseg = 1;
-        d.seg[0] = IgSeg{0, 0, 0, 0, 0, 0, kchunks};
-        d.Wt = hp(vT) + static_cast<size_t>(b) * C * T; d.N = C; d.K = T;
-        d.k_ragged = 1;
-        d.bias = dry ? nullptr : e.F(key + ".to_v.bias");
-        d.out = hp(o) + static_cast<size_t>(b) * T * C; d.ld_out = C;
-        add_igemm(key + ".pv", d);
-      }
-    }
-    ar.free(s_off);
-    ar.free(p_off);
+    Act qkv = linear(key + ".qkv", n, nullptr, key + ".qkv", 3 * C, true, nullptr);  // [M, q | k | v]
     release(n);
-    release(qk);
-    release(vT);
+    Act o = alloc(B, x.H, x.W, C);
+    {
+      AttnDesc d;
+      d.B = B; d.heads = 1; d.D = C; d.Tq = T; d.Tk = T;
+      d.q = hp(qkv); d.k = hp(qkv) + C; d.v = hp(qkv) + 2 * C;
+      d.ld_q = d.ld_k = d.ld_v = 3 * C;
+      d.bs_q = d.bs_k = d.bs_v = static_cast<long long>(T) * 3 * C;
+      d.out = hp(o); d.ld_out = C;
+      add_attn(key, d);
+    }
+    release(qkv);
     Act out = linear(key + ".to_out.0", o, nullptr, key + ".to_out.0", C, true, &x);
     release(o);
     return out;

@@ -240,10 +240,19 @@ def test_vae_encode_parity(engine, vae_weights_gpu):
         torch.testing.assert_close(z, sd15.vae_sample(m, lv, eps.to(DEV)), atol=1e-5, rtol=1e-5)
 
 
-def test_vae_unsupported_size_fails_loudly(engine):
-    """(H/8)*(W/8) not a multiple of 8 is not supported by the unfused VAE attention: error, never a fallback"""
-    with pytest.raises(RuntimeError, match="multiple of 8"):
-        engine.vae_encode(torch.zeros(1, 3, 72, 40))
+def test_vae_encode_any_size(engine, vae_weights_gpu):
+    """the reference encodes arbitrary image sizes (geo / ftt images are not rescaled, compute.py:165-180): token counts
+    that are not multiples of 8 (72x40 -> 45 tokens) or of the 128-row query tile go through the single-head flash kernel"""
+    for (B, H, W) in [(1, 72, 40), (2, 200, 136), (1, 8, 8)]:
+        g = torch.Generator().manual_seed(B + H + W)
+        img = torch.rand(B, 3, H, W, generator=g) * 2 - 1
+        with torch.no_grad():
+            m_g, lv_g = sd15.vae_encode_moments(vae_weights_gpu, img.to(DEV))
+            m_a, lv_a = sd15.vae_encode_moments(half_weights(vae_weights_gpu), img.to(DEV), autocast=True)
+        _, m, lv = engine.vae_encode(img, None, return_moments=True)
+        assert m.shape == m_g.shape == (B, 4, H // 8, W // 8)
+        noise_floor_gate(m, m_g, m_a, f"vae mean {H}x{W}")
+        noise_floor_gate(lv, lv_g, lv_a, f"vae logvar {H}x{W}")
 
 
 def test_dift_parity(engine, unet_weights_gpu, contexts):

@@ -203,6 +203,22 @@ def test_flash_attention_non_persistent_variant(lib, case):
             check(lib, lib.dm_op_set_variant(b"attn3", -1))
 
 
+@pytest.mark.parametrize("B,T", [(2, 1024), (1, 45), (3, 425), (1, 4096)])
+def test_vae_single_head_attention(lib, B, T):
+    """one 512-wide head (VAE mid block) on the flash kernel: two CTAs per query tile, any token count"""
+    C = 512
+    g = torch.Generator(device="cuda").manual_seed(40 + B + T)
+    qkv = torch.randn(B, T, 3 * C, device="cuda", generator=g).half()
+    out = torch.full((B, T, C), float("nan"), device="cuda", dtype=torch.float16)
+    check(lib, lib.dm_op_attention(ptr(qkv[..., :C]), ptr(qkv[..., C:2 * C]), ptr(qkv[..., 2 * C:]), 3 * C, 3 * C, 3 * C,
+                                   T * 3 * C, T * 3 * C, T * 3 * C, B, 1, C, T, T, 0, None, ptr(out), C, stream()))
+    torch.cuda.synchronize()
+    q, k, v = [t.float().reshape(B, T, 1, C).transpose(1, 2) for t in (qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:])]
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, T, C)
+    assert torch.isfinite(out).all()
+    assert max_rel(out, ref) < 2e-3
+
+
 def test_attention_large_logits(lib):
     """peaked softmax (|logit| ~ 50): the running-max rescale path in TMEM must stay exact"""
     B, T, D, heads = 1, 512, 40, 8
