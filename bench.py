@@ -10,6 +10,10 @@
     (52.5 TFLOP / image).  One "sample" = one image scored.
 --config 3 (configs[2]): DIFT-161 features, t=161: per GPU and step 8 images 512x512 x ensemble 8 = 64 members
     (one VAE encode per image, 64 partial U-Net forwards through up_blocks[1]); unit = members/s.
+--config 4 (configs[3], meant for --gpus 8): 10 000 synthetic 512x512 images in total, sharded over the ranks (rank r takes
+    images r::world as compute.py:336-341 does), 10 "country" prompts + uncond resident as contexts, every image scored with 32
+    draws x {its country, uncond}; per-image raw grids stay rank-local, the T maps of all 10 000 images are gathered with ONE
+    all-gather at the end of the step (164 MB).  Fixed total work: "scaling": "strong".  One step = the whole data set.
 --config 5 (configs[4]): 1024x1024 image, 14 conditions + uncond batched in one call, 16 (eps,t) draws = 240 U-Net
     forwards at 128x128 latents + 1 VAE encode per image (1126.6 TFLOP / image); one image per GPU and step.
 Weak scaling everywhere: every rank works on its own inputs; for the typicality configs the only exchange is the
@@ -250,6 +254,119 @@ class Typicality:
         return v, sample
 
 
+class Geo:
+    """config 4: the whole 10k-image data set per step, sharded; one all-gather of the T maps at the end"""
+
+    def __init__(self):
+        self.metric = "typicality samples/sec (512x512, 32 t-steps, cond+uncond)"
+        self.unit = "samples/s"
+        self.total = int(os.environ.get("DM_BENCH_C4_IMAGES", "10000"))
+        self.draws_n, self.n_cond, self.img, self.lat, self.cap, self.chunk = 32, 2, 512, 64, 56, 16
+        self.n_countries = 10
+        self.flop_per_unit = 64 * 803.3e9 + 1116.7e9
+        self.workload = (f"configs[3]: {self.total} synthetic 512x512 RGB images in total, sharded i::world, 10 country prompts + uncond, 32 (eps,t) "
+                         "draws x {country, uncond} per image = 64 U-Net forwards @64x64 + 1 VAE encode; ONE all-gather of all T maps per step")
+
+    def setup(self, torch, eng, dev, rank, world):
+        from diff_mining_b200 import parallel
+
+        self.torch, self.eng, self.dev, self.world, self.rank = torch, eng, dev, world, rank
+        ctxs = make_contexts(torch, self.n_countries + 1)
+        for i, c in enumerate(ctxs):
+            eng.set_context(i, c)
+        self.ctxs = ctxs
+        self.mine = parallel.shard_indices(self.total, world, rank)
+        self.images = len(self.mine)
+        # uint8 images, as a loader would hand them over (load_image: to_tensor * 2 - 1 happens on the device)
+        g = torch.Generator().manual_seed(4000 + rank)
+        pool = torch.randint(0, 256, (64, 3, self.img, self.img), generator=g, dtype=torch.uint8)
+        self.imgs_host = pool.pin_memory()       # 64 distinct images, cycled: content does not change the work
+        self.imgs_dev = self.imgs_host.to(dev)
+        self.grid_host = [torch.empty(self.chunk, self.draws_n, 2, 4, self.lat, self.lat, dtype=torch.float16).pin_memory() for _ in range(2)]
+        self.T_host = torch.empty(self.total, self.lat, self.lat, dtype=torch.float32).pin_memory()
+        self.copy_stream = torch.cuda.Stream(dev)
+        # images of one country are scored together (2 conditions per image: its country and uncond, parallel-dataset/compute.py:153-154)
+        self.chunks = []
+        for c in range(self.n_countries):
+            loc = [k for k, i in enumerate(self.mine) if i % self.n_countries == c]
+            self.chunks += [(c, loc[a:a + self.chunk]) for a in range(0, len(loc), self.chunk)]
+
+    def draws(self):
+        torch, dev = self.torch, self.dev
+        torch.manual_seed(42)
+        x = torch.empty(1, 4, self.lat, self.lat, device=dev)
+        ns, ts = zip(*[(torch.randn_like(x), torch.randint(100, 700, (1,), device=dev)) for _ in range(self.draws_n)])
+        return torch.cat(ns), torch.cat(ts).long()
+
+    def _run(self, e2e):
+        torch = self.torch
+        from diff_mining_b200 import parallel
+
+        T_local = torch.empty(self.images, self.lat, self.lat, device=self.dev)
+        noise, t = self.draws()
+        evs = [None, None]
+        for ci, (c, loc) in enumerate(self.chunks):
+            sel = torch.tensor([k % 64 for k in loc])
+            if e2e:
+                u8 = self.imgs_host[sel].pin_memory().to(self.dev, non_blocking=True)
+            else:
+                u8 = self.imgs_dev[sel.to(self.dev)]
+            imgs = u8.float().div_(255.0).mul_(2).sub_(1)
+            post = torch.randn(len(loc), 4, self.lat, self.lat, device=self.dev, dtype=torch.float16)
+            x0 = self.eng.vae_encode(imgs, post)
+            grid, T = self.eng.typicality(x0, noise, t, [1 + c, 0], max_forwards=self.cap)
+            T_local[torch.tensor(loc, device=self.dev)] = T[:, 0]
+            if e2e:   # the per-image .npy payloads leave the device through a double-buffered pinned ring on a side stream
+                b = ci & 1
+                if evs[b] is not None:
+                    evs[b].synchronize()
+                done = torch.cuda.Event()
+                done.record()
+                with torch.cuda.stream(self.copy_stream):
+                    self.copy_stream.wait_event(done)
+                    self.grid_host[b][: len(loc)].copy_(grid, non_blocking=True)
+                    grid.record_stream(self.copy_stream)
+                    evs[b] = torch.cuda.Event()
+                    evs[b].record(self.copy_stream)
+        Tall = parallel.gather_tmaps(T_local, self.total) if self.world > 1 else T_local   # the ONE collective of the step
+        if e2e:
+            torch.cuda.current_stream().wait_stream(self.copy_stream)
+            self.T_host.copy_(Tall, non_blocking=True)
+            return self.grid_host[0], self.T_host
+        return T_local, Tall
+
+    def step_resident(self):
+        return self._run(False)
+
+    def step_e2e(self):
+        return self._run(True)
+
+    def finish(self):
+        pass
+
+    def bytes_per_step(self):
+        return self.images * 3 * self.img * self.img, self.images * self.draws_n * 2 * 4 * self.lat * self.lat * 2 + self.total * self.lat * self.lat * 4
+
+    @property
+    def units(self):
+        return self.images
+
+    def plan(self):
+        return "unet", balanced_microbatch(self.chunk * self.draws_n * 2, self.cap, 2), self.lat, self.lat, 2
+
+    def config(self):
+        return {"workload": self.workload, "images_total": self.total, "images_this_rank": self.images, "mc_samples": self.draws_n, "n_cond": 2,
+                "contexts_resident": self.n_countries + 1, "micro_batch_forwards": self.plan()[1],
+                "l2": "inputs larger than L2: each micro-batch streams 1.72 GB of weights + >1 GB of activations through a 126 MB L2; no explicit flush"}
+
+    def check(self, out):
+        assert self.torch.isfinite(out[1]).all()
+
+    cpu_sample = Typicality.cpu_sample
+    cfg = 2
+    images_cfg = None
+
+
 class Dift:
     """config 3: SDFeaturizer.forward on 8 images x ensemble 8 (64 members per step)"""
 
@@ -326,9 +443,11 @@ class Dift:
 def make_workload(cfg):
     if cfg in (2, 5):
         return Typicality(cfg)
+    if cfg == 4:
+        return Geo()
     if cfg == 3:
         return Dift()
-    raise SystemExit(f"--config must be 2, 3 or 5 (got {cfg})")
+    raise SystemExit(f"--config must be 2, 3, 4 or 5 (got {cfg})")
 
 
 # ----------------------------------------------------------------------------------------------- arms
@@ -390,7 +509,7 @@ def run_ours(args):
     wl = make_workload(args.config)
     wl.setup(torch, eng, dev, rank, world)
     units = getattr(wl, "units", None) or wl.images
-    n_total = units * world
+    n_total = wl.total if args.config == 4 else units * world   # config 4: fixed total work (strong scaling)
 
     def barrier():
         if world > 1:
@@ -413,7 +532,15 @@ def run_ours(args):
         return ms.item() / steps, eng.launch_count - l0, out
 
     warm = max(args.warmup, 3)
-    for _ in range(warm):
+    if args.config == 4:
+        # one step = the whole data set (minutes): warm up on three chunks instead of three full passes
+        full, wl.chunks = wl.chunks, wl.chunks[:3]
+        for _ in range(warm):
+            wl.step_resident()
+            wl.step_e2e()
+        wl.chunks = full
+        warm_note = f"{warm} x 3 chunks of 16 images (a full pass is one timed step)"
+    for _ in range(0 if args.config == 4 else warm):
         wl.step_resident()
     wl.finish()
     clocks = ClockSampler(local)
@@ -421,7 +548,7 @@ def run_ours(args):
     ms_step, launches, out = timed(wl.step_resident, args.steps)
     clk = clocks.stop()
     wl.check(out)
-    for _ in range(2):
+    for _ in range(0 if args.config == 4 else 2):
         wl.step_e2e()
     wl.finish()
     ms_e2e, _, out_e2e = timed(wl.step_e2e, args.steps)
@@ -431,8 +558,10 @@ def run_ours(args):
     pk = load_peaks()
     cfg = wl.config()
     cfg["parallelism"] = f"dp{world} (image sharding" + (", one async all-gather of T maps per step)" if args.config != 3 else ")")
+    if args.config == 4:
+        cfg["warmup_note"] = warm_note
     line = {"metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps, "warmup": warm,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.config == 4 else "weak", "vs_baseline": None, "dtype": "fp16",
             "data": "synthetic", "config": cfg, "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": n_total / (ms_e2e * 1e-3), "unit": wl.unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "tensor_roofline_frac_whole_step": value / world * wl.flop_per_unit / 1e12 / pk["tflops"]}
@@ -469,7 +598,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -56,7 +56,10 @@ __device__ __forceinline__ uint32_t bf16_round_up_bits(float x) {
 }
 
 // VAR (tuning switches, bit mask): 1 = hand the XU token over two chunks before the end of the exponential phase,
-// 2 = no XU token (groups run free), 4 = helper roles poll with the suspend-time hint, 8 = L2 prefetch of the next Q
+// 2 = no XU token (groups run free), 4 = helper roles poll with the suspend-time hint, 8 = L2 prefetch of the next Q,
+// 32 = the exponential loop is software-pipelined in the source (the MUFUs of chunk c+1 are issued before chunk c is packed),
+// 64 = two-pass S: the scores are read from TMEM once for the row maximum and again, 16 columns at a time, inside the
+//      exponential phase (32 instead of 64 live score registers there; S is released at the end of the phase)
 template <int D, int BKV, int ST, int VAR>
 __global__ void __launch_bounds__(640, 1) attention3_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
   using Cfg = Attn3Cfg<D, BKV, ST>;
@@ -277,25 +280,49 @@ __global__ void __launch_bounds__(640, 1) attention3_kernel(const __grid_constan
         const uint32_t gp = G & 1;
         mbar_wait(&s_full[wg], gp);
         tc_fence_after();
-        uint32_t raw[HC];
-#pragma unroll
-        for (int c0 = 0; c0 < HC; c0 += 32) tmem_ld_x32(t_s + c0, raw + c0);
-        tmem_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[wg]);
-
         const int kbase = j * BKV + half * HC;
-        if (kbase + HC > p.Tk) {  // ragged last tile
+        const bool ragged = kbase + HC > p.Tk;  // ragged last tile
+        uint32_t raw[(VAR & 64) ? 1 : HC];
+        float mx0, mx1;
+        if constexpr ((VAR & 64) != 0) {
+          // pass 1: row maximum only, 32 columns at a time; S stays in tensor memory for the exponential phase
+          mx0 = -INFINITY;
+          mx1 = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < HC; ++i)
-            if (kbase + i >= p.Tk) raw[i] = 0xff800000u;  // -inf
-        }
-        float mx0 = __uint_as_float(raw[0]), mx1 = __uint_as_float(raw[1]);
+          for (int c0 = 0; c0 < HC; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_x32(t_s + c0, r);
+            tmem_wait_ld();
+            if (ragged) {
 #pragma unroll
-        for (int i = 2; i < HC; i += 4) {
-          mx0 = fmax3(mx0, __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
-          if (i + 2 < HC) mx1 = fmax3(mx1, __uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]));
+              for (int i = 0; i < 32; ++i)
+                if (kbase + c0 + i >= p.Tk) r[i] = 0xff800000u;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              mx0 = fmax3(mx0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+              mx1 = fmax3(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c0 = 0; c0 < HC; c0 += 32) tmem_ld_x32(t_s + c0, raw + c0);
+          tmem_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[wg]);
+          if (ragged) {
+#pragma unroll
+            for (int i = 0; i < HC; ++i)
+              if (kbase + i >= p.Tk) raw[i] = 0xff800000u;  // -inf
+          }
+          mx0 = __uint_as_float(raw[0]);
+          mx1 = __uint_as_float(raw[1]);
+#pragma unroll
+          for (int i = 2; i < HC; i += 4) {
+            mx0 = fmax3(mx0, __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+            if (i + 2 < HC) mx1 = fmax3(mx1, __uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]));
+          }
         }
         // the row's other half lives in the partner thread (warp + 4): both publish their half-row maximum rounded up to
         // bf16 and take the larger one, so the two threads always agree on the reference maximum
@@ -339,23 +366,87 @@ __global__ void __launch_bounds__(640, 1) attention3_kernel(const __grid_constan
             else if (j + 1 < nkv) asm volatile("bar.arrive 4, 512;" ::: "memory");
           }
         };
-#pragma unroll
-        for (int c0 = 0; c0 < HC; c0 += 8) {
-          if constexpr ((VAR & 1) != 0) {
-            if (c0 == HC - 16) pass_token();  // the other group's start-up overlaps the tail of this exponential phase
-          }
-          uint32_t pk[4];
+        auto ex8 = [&](int c0, float* o) {
 #pragma unroll
           for (int i = 0; i < 8; i += 2) {
             const uint64_t x =
                 fma_f2(pack_f2(__uint_as_float(raw[c0 + i]), __uint_as_float(raw[c0 + i + 1])), sc2, off2);
             float e0, e1;
             unpack_f2(x, e0, e1);
-            pk[i >> 1] = pack_h2(fast_exp2(e0), fast_exp2(e1));
+            o[i] = fast_exp2(e0);
+            o[i + 1] = fast_exp2(e1);
           }
+        };
+        auto st8 = [&](int c0, const float* v) {
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pbase ^ static_cast<uint32_t>((c0 >> 3) << 4)),
-                       "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                       "r"(pack_h2(v[0], v[1])), "r"(pack_h2(v[2], v[3])), "r"(pack_h2(v[4], v[5])), "r"(pack_h2(v[6], v[7]))
                        : "memory");
+        };
+        if constexpr ((VAR & 64) != 0) {
+          // pass 2: 16 score columns at a time, the next block's TMEM load in flight under the exponentials of this one
+          constexpr int BW = 16, NB = HC / BW;
+          uint32_t blk[2][BW];
+          auto ex8r = [&](const uint32_t* r, float* o) {
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              const uint64_t x = fma_f2(pack_f2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc2, off2);
+              float e0, e1;
+              unpack_f2(x, e0, e1);
+              o[i] = fast_exp2(e0);
+              o[i + 1] = fast_exp2(e1);
+            }
+          };
+          tmem_ld_x16(t_s, blk[0]);
+          tmem_wait_ld();
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) {
+            uint32_t* cur = blk[nb & 1];
+            if (nb + 1 < NB) tmem_ld_x16(t_s + (nb + 1) * BW, blk[(nb + 1) & 1]);
+            if (ragged) {
+#pragma unroll
+              for (int i = 0; i < BW; ++i)
+                if (kbase + nb * BW + i >= p.Tk) cur[i] = 0xff800000u;
+            }
+            float e[8], f[8];
+            ex8r(cur, e);
+            ex8r(cur + 8, f);
+            st8(nb * BW, e);
+            st8(nb * BW + 8, f);
+            if (nb + 1 < NB) {
+              tmem_wait_ld();
+              if (nb + 2 == NB) {  // the last block of S is in registers: QK^T of the next tile may overwrite it
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_free[wg]);
+              }
+            }
+          }
+          if constexpr (NB == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[wg]);
+          }
+        } else if constexpr ((VAR & 32) != 0) {
+          float ea[8], eb[8];
+          ex8(0, ea);
+#pragma unroll
+          for (int c0 = 8; c0 < HC; c0 += 16) {
+            ex8(c0, eb);
+            st8(c0 - 8, ea);
+            if (c0 + 8 < HC) ex8(c0 + 8, ea);
+            st8(c0, eb);
+          }
+          if constexpr ((HC / 8) % 2 == 1) st8(HC - 8, ea);
+        } else {
+#pragma unroll
+          for (int c0 = 0; c0 < HC; c0 += 8) {
+            if constexpr ((VAR & 1) != 0) {
+              if (c0 == HC - 16) pass_token();  // the other group's start-up overlaps the tail of this exponential phase
+            }
+            float e[8];
+            ex8(c0, e);
+            st8(c0, e);
+          }
         }
         if constexpr ((VAR & 1) == 0) pass_token();
         fence_proxy_async_smem();

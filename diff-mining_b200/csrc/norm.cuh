@@ -250,7 +250,9 @@ __global__ void __launch_bounds__(384) gn_apply_kernel(NormSrc s0, NormSrc s1, i
 //           per-CTA sums of squared deviations about those means -> variances
 //   pass 2  the slice is read again -- an L2 hit, it was streamed a few microseconds ago -- normalised (+SiLU) and
 //           written.  HBM traffic = 1 read + 1 write of the activation (the two-kernel path reads it twice).
-__global__ void __launch_bounds__(384) gn_fused_kernel(NormSrc s0, NormSrc s1, int HW, int cpg, int px_per, int VT, int R,
+// MINB = co-resident CTAs per SM the register budget is held to, UNR = independent 16-byte loads in flight per thread
+template <int MINB, int UNR>
+__global__ void __launch_bounds__(384, MINB) gn_fused_kernel(NormSrc s0, NormSrc s1, int HW, int cpg, int px_per, int VT, int R,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float eps, int silu, __half* __restrict__ out) {
   namespace cg = cooperative_groups;
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(384) gn_fused_kernel(NormSrc s0, NormSrc s1, i
 #pragma unroll
     for (int i = 0; i < 8; ++i) { a[i] = 0.f; q[i] = 0.f; }
     gn_unpack8(__ldg(reinterpret_cast<const uint4*>(base)), k);
-    gn_accumulate<8>(base, ps, p0, p1, r, R, k, a, q);
+    gn_accumulate<UNR>(base, ps, p0, p1, r, R, k, a, q);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       sm_a[threadIdx.x * 8 + i] = a[i];  // index = r*C + channel
@@ -338,12 +340,12 @@ __global__ void __launch_bounds__(384) gn_fused_kernel(NormSrc s0, NormSrc s1, i
     *reinterpret_cast<uint4*>(obase + static_cast<long long>(px) * C) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   };
   int px = p0 + r;
-  for (; px + 7 * R < p1; px += 8 * R) {
-    uint4 u[8];
+  for (; px + (UNR - 1) * R < p1; px += UNR * R) {
+    uint4 u[UNR];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) u[k] = __ldcg(reinterpret_cast<const uint4*>(base + (px + k * R) * ps));
+    for (int k = 0; k < UNR; ++k) u[k] = __ldcg(reinterpret_cast<const uint4*>(base + (px + k * R) * ps));
 #pragma unroll
-    for (int k = 0; k < 8; ++k) apply(u[k], px + k * R);
+    for (int k = 0; k < UNR; ++k) apply(u[k], px + k * R);
   }
   for (; px < p1; px += R) apply(__ldcg(reinterpret_cast<const uint4*>(base + px * ps)), px);
 }

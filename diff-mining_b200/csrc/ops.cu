@@ -420,21 +420,14 @@ void attn_launch(const AttnOp& op, cudaStream_t s) {
     const int var = variant_attn3() - 1;
     if (op.D == 40) {
       switch (var) {
-        case 1: attn3_launch_d<40, 128, 2, 1>(op, s); break;
-        case 2: attn3_launch_d<40, 128, 2, 2>(op, s); break;
-        case 4: attn3_launch_d<40, 128, 2, 4>(op, s); break;
-        case 5: attn3_launch_d<40, 128, 2, 5>(op, s); break;
-        case 8: attn3_launch_d<40, 128, 2, 8>(op, s); break;
-        case 12: attn3_launch_d<40, 128, 2, 12>(op, s); break;
-        case 13: attn3_launch_d<40, 128, 2, 13>(op, s); break;
-        case 14: attn3_launch_d<40, 128, 2, 14>(op, s); break;
+        case 32: attn3_launch_d<40, 128, 2, 32>(op, s); break;
+        case 64: attn3_launch_d<40, 128, 2, 64>(op, s); break;
         default: attn3_launch_d<40, 128, 2, 0>(op, s); break;
       }
     } else {
       switch (var) {
-        case 13: attn3_launch_d<80, 64, 3, 13>(op, s); break;
-        case 12: attn3_launch_d<80, 64, 3, 12>(op, s); break;
-        case 14: attn3_launch_d<80, 64, 3, 14>(op, s); break;
+        case 32: attn3_launch_d<80, 64, 3, 32>(op, s); break;
+        case 64: attn3_launch_d<80, 64, 3, 64>(op, s); break;
         default: attn3_launch_d<80, 64, 3, 0>(op, s); break;
       }
     }
@@ -506,10 +499,7 @@ void gn_launch(const GnDesc& d, cudaStream_t s) {
     static const int cl_max = env_or("DM_GN_CLUSTER", 8);  // 16 measured 8 % slower (r01)
     int CL = d.HW >= 2048 ? 16 : d.HW >= 512 ? 8 : d.HW >= 256 ? 4 : d.HW >= 128 ? 2 : 1;
     CL = std::min(CL, cl_max);
-    static bool configured[64] = {};
-    if (first_use_on_this_device(configured)) {
-      DM_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      }
+    static const int gn_var = env_or("DM_GN_VAR", 0);  // tuning: 0 = (1 CTA/SM register budget, 8 loads), 1 = (3, 4), 2 = (2, 8), 3 = (3, 6)
     const int px_per = (d.HW + CL - 1) / CL;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(CL, d.Nimg, 1);
@@ -523,8 +513,17 @@ void gn_launch(const GnDesc& d, cudaStream_t s) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DM_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel, s0, s1, d.HW, cpg, px_per, g.VT, g.R, d.gamma, d.beta, d.eps, d.silu,
-                               d.out));
+    auto go = [&](auto kernel) {
+      static bool configured[64] = {};
+      if (first_use_on_this_device(configured)) DM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      DM_CUDA(cudaLaunchKernelEx(&cfg, kernel, s0, s1, d.HW, cpg, px_per, g.VT, g.R, d.gamma, d.beta, d.eps, d.silu, d.out));
+    };
+    switch (gn_var) {
+      case 1: go(gn_fused_kernel<3, 4>); break;
+      case 2: go(gn_fused_kernel<2, 8>); break;
+      case 3: go(gn_fused_kernel<3, 6>); break;
+      default: go(gn_fused_kernel<1, 8>); break;
+    }
     return;
   }
   gn_stats_kernel<<<dim3(g.splits, d.Nimg), g.threads, std::max<size_t>(smem, 256), s>>>(
