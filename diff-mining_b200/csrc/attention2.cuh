@@ -36,7 +36,7 @@ struct Attn2Cfg {
   static constexpr int Q_TILE_BYTES = NCH * 128 * 128;
   static constexpr int KV_BYTES = NCH * BKV * 128;
   static constexpr int P_TILE_BYTES = 128 * BKV * 2;  // one P buffer; two per Q tile
-  static constexpr int NBAR = 1 + 4 * ST + 10;
+  static constexpr int NBAR = 1 + 4 * ST + 12;
   static constexpr int SMEM_BYTES = 2 * Q_TILE_BYTES + 2 * ST * KV_BYTES + 4 * P_TILE_BYTES + NBAR * 8 + 64;
   // Half-row exchange slots live in the never-read tail of the Q tile: logical 16-byte chunk 6 of every 128-byte
   // row of the last 64-channel chunk holds channels >= 48 (+64*(NCH-1)), which no MMA touches.
@@ -96,8 +96,9 @@ __global__ void __launch_bounds__(640, 1) attention2_kernel(const __grid_constan
   uint64_t* v_empty = v_full + ST;
   uint64_t* s_full = v_empty + ST;  // [q]
   uint64_t* s_free = s_full + 2;    // [q]
-  uint64_t* p_full = s_free + 2;    // [q]
-  uint64_t* o_full = p_full + 2;    // [q][buf]
+  uint64_t* p_full = s_free + 2;    // [q][buf]: per P buffer (a single barrier could be lapped: the softmax may finish tile j+1
+                                    // before the issuer has waited for tile j)
+  uint64_t* o_full = p_full + 4;    // [q][buf]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -118,7 +119,8 @@ __global__ void __launch_bounds__(640, 1) attention2_kernel(const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_free[i], 8);
-      mbar_init(&p_full[i], 8);
+      mbar_init(&p_full[2 * i], 8);
+      mbar_init(&p_full[2 * i + 1], 8);
       mbar_init(&o_full[2 * i], 1);
       mbar_init(&o_full[2 * i + 1], 1);
     }
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(640, 1) attention2_kernel(const __grid_constan
         }
         const int st = j % ST;
         mbar_wait(&v_full[st], (j / ST) & 1);
-        mbar_wait(&p_full[q], jp);  // P_q(j) in smem buffer j&1, O_q rescaled
+        mbar_wait(&p_full[2 * q + jp], (j >> 1) & 1);  // P_q(j) in smem buffer j&1, O_q rescaled
         tc_fence_after();
         issue_pv(st, jp, j == 0);
         umma_commit(&o_full[2 * q + jp]);
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(640, 1) attention2_kernel(const __grid_constan
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[wg]);
+      if (lane == 0) mbar_arrive(&p_full[2 * wg + jp]);
     }
 
     // ---- epilogue: O / l -> fp16; the two threads of a row add their half-row sums and split the head dim

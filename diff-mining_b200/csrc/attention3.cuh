@@ -35,7 +35,7 @@ struct Attn3Cfg {
   static constexpr int V_BYTES = NCHV * BKV * 128;
   static constexpr int P_TILE_BYTES = 128 * BKV * 2;      // one P buffer; two per Q tile
   static constexpr int XCH_BYTES = 2 * 2 * 128 * 2 * 2;   // [group][parity][row][half] bf16 half-row maxima
-  static constexpr int NBAR = 2 + 5 * ST + 12;
+  static constexpr int NBAR = 2 + 5 * ST + 14;
   static constexpr int SMEM_BYTES = 2 * Q_TILE_BYTES + ST * (K_BYTES + V_BYTES) + 4 * P_TILE_BYTES + XCH_BYTES + NBAR * 8 + 64;
   static constexpr int HC = BKV / 2;                      // key columns per softmax thread
   static constexpr int O_COL = 2 * BKV;                   // S_q at columns [q*BKV, (q+1)*BKV), O_q at O_COL + q*DKL
@@ -81,8 +81,9 @@ __global__ void __launch_bounds__(640, 1) attention3_kernel(const __grid_constan
   uint64_t* v_empty = v_ready + ST;
   uint64_t* s_full = v_empty + ST;  // [q]
   uint64_t* s_free = s_full + 2;    // [q]
-  uint64_t* p_full = s_free + 2;    // [q]
-  uint64_t* o_full = p_full + 2;    // [q][buf]
+  uint64_t* p_full = s_free + 2;    // [q][buf]: one barrier per P buffer -- the softmax may run a whole tile ahead of the
+                                    // issuer, and a single barrier two completions ahead would alias its phase parity
+  uint64_t* o_full = p_full + 4;    // [q][buf]
   uint64_t* o_free = o_full + 4;    // [q]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
@@ -115,7 +116,8 @@ __global__ void __launch_bounds__(640, 1) attention3_kernel(const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_free[i], 8);
-      mbar_init(&p_full[i], 8);
+      mbar_init(&p_full[2 * i], 8);
+      mbar_init(&p_full[2 * i + 1], 8);
       mbar_init(&o_full[2 * i], 1);
       mbar_init(&o_full[2 * i + 1], 1);
       mbar_init(&o_free[i], 8);
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(640, 1) attention3_kernel(const __grid_constan
           }
           const int st = G % ST;
           hwait(&v_ready[st], (G / ST) & 1);  // V tile landed and its ones column written
-          hwait(&p_full[q], gp);              // P_q in smem buffer G&1, O_q rescaled
+          hwait(&p_full[2 * q + gp], (G >> 1) & 1);  // P_q in smem buffer G&1, O_q rescaled
           if (j == 0 && lw > 0) hwait(&o_free[q], (lw - 1) & 1);  // the epilogue of the previous work item has read O_q
           tc_fence_after();
           issue_pv(st, gp, j == 0);
@@ -452,7 +454,7 @@ __global__ void __launch_bounds__(640, 1) attention3_kernel(const __grid_constan
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[wg]);
+        if (lane == 0) mbar_arrive(&p_full[2 * wg + gp]);
       }
 
       // ---- epilogue of the work item: O / l -> fp16; the two threads of a row split the head dim; l = TMEM column D

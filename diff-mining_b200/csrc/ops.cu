@@ -499,7 +499,7 @@ void gn_launch(const GnDesc& d, cudaStream_t s) {
     static const int cl_max = env_or("DM_GN_CLUSTER", 8);  // 16 measured 8 % slower (r01)
     int CL = d.HW >= 2048 ? 16 : d.HW >= 512 ? 8 : d.HW >= 256 ? 4 : d.HW >= 128 ? 2 : 1;
     CL = std::min(CL, cl_max);
-    static const int gn_var = env_or("DM_GN_VAR", 0);  // tuning: 0 = (1 CTA/SM register budget, 8 loads), 1 = (3, 4), 2 = (2, 8), 3 = (3, 6)
+    static const int gn_var = env_or("DM_GN_VAR", 2);  // (CTAs per SM the registers are capped for, loads in flight): 0 = (1, 8), 1 = (3, 4), 2 = (2, 8) [default: -4.6 % measured], 3 = (3, 6)
     const int px_per = (d.HW + CL - 1) / CL;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(CL, d.Nimg, 1);
