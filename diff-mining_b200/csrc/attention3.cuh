@@ -12,10 +12,12 @@
 //   warp 3       writes a column of ONES at channel D of every landed V tile (the padding column TMA zero-filled), so the
 //                PV MMA itself accumulates the row sums l = sum_k P in TMEM column D of O: the softmax warps carry no
 //                row-sum arithmetic and no second exchange (and l is the sum of the fp16-rounded P the numerator uses)
-//   warps 4-11   softmax group 0 (tile 0): TWO threads per query row, each owning half of the key columns
-//   warps 12-19  softmax group 1 (tile 1)
-// The two threads of a row agree on the running maximum through one 16-bit shared-memory slot each (the half-row max
-// rounded UP to bf16 precision: any common value >= the true max keeps the softmax exact after normalisation).
+//   TPR = 2:  warps 4-11 softmax group 0 (tile 0), warps 12-19 group 1 (tile 1): TWO threads per query row, each owning
+//             half of the key columns; the two threads of a row agree on the running maximum through one 16-bit
+//             shared-memory slot each (the half-row max rounded UP to bf16 precision: any common value >= the true max
+//             keeps the softmax exact after normalisation)
+//   TPR = 1:  warps 4-7 / 8-11: ONE thread per query row (no exchange, fewer instructions per element, up to 168
+//             registers per thread)
 // S is pulled into registers in one TMEM pass and released at once, P is double-buffered in shared memory, O is rescaled
 // in TMEM only when the row max grew by more than 2^8 (lazy rescale), and the two groups alternate their exponential
 // phases through an "XU token" (named barriers 4 / 5) exactly as in attention2.
@@ -24,7 +26,7 @@
 
 namespace dm {
 
-template <int D, int BKV, int ST>
+template <int D, int BKV, int ST, int TPR = 2>
 struct Attn3Cfg {
   static constexpr int DK = (D + 15) / 16 * 16;           // K extent of QK^T
   static constexpr int DKL = DK > D ? DK : DK + 16;       // N extent of the PV MMA: head_dim + the ones column at channel D
@@ -34,15 +36,16 @@ struct Attn3Cfg {
   static constexpr int K_BYTES = NCH * BKV * 128;
   static constexpr int V_BYTES = NCHV * BKV * 128;
   static constexpr int P_TILE_BYTES = 128 * BKV * 2;      // one P buffer; two per Q tile
-  static constexpr int XCH_BYTES = 2 * 2 * 128 * 2 * 2;   // [group][parity][row][half] bf16 half-row maxima
+  static constexpr int XCH_BYTES = 2 * 2 * 128 * 2 * 2;   // [group][parity][row][half] bf16 half-row maxima (TPR = 2)
   static constexpr int NBAR = 2 + 5 * ST + 14;
   static constexpr int SMEM_BYTES = 2 * Q_TILE_BYTES + ST * (K_BYTES + V_BYTES) + 4 * P_TILE_BYTES + XCH_BYTES + NBAR * 8 + 64;
-  static constexpr int HC = BKV / 2;                      // key columns per softmax thread
+  static constexpr int HC = BKV / TPR;                    // key columns per softmax thread
   static constexpr int O_COL = 2 * BKV;                   // S_q at columns [q*BKV, (q+1)*BKV), O_q at O_COL + q*DKL
   static constexpr int TMEM_COLS = 512;
-  static constexpr int THREADS = 128 + 512;
+  static constexpr int THREADS = 128 + 256 * TPR;
   // position of the ones column inside a V tile row: chunk, 16-byte piece, byte inside the piece
   static constexpr int ONE_CHUNK = D / 64, ONE_PIECE = (D % 64) / 8, ONE_BYTE = (D % 8) * 2;
+  static_assert(TPR == 1 || TPR == 2, "threads per query row");
   static_assert(NCHV == NCH, "V tile must have the same chunk count as K (shared ring stride)");
   static_assert(2 * BKV + 2 * DKL <= 512, "TMEM budget");
   static_assert(BKV == 64 || BKV == 128, "BKV");
@@ -54,16 +57,21 @@ __device__ __forceinline__ uint32_t bf16_round_up_bits(float x) {
   const uint32_t u = __float_as_uint(x);
   return (static_cast<int32_t>(u) >= 0) ? ((u + 0xFFFFu) >> 16) : (u >> 16);  // negatives: truncation moves toward +inf
 }
+template <int ID, int NT>
+__device__ __forceinline__ void nbar_sync() {
+  asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NT) : "memory");
+}
+template <int ID, int NT>
+__device__ __forceinline__ void nbar_arrive() {
+  asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(NT) : "memory");
+}
 
-// VAR (tuning switches, bit mask): 1 = hand the XU token over two chunks before the end of the exponential phase,
-// 2 = no XU token (groups run free), 4 = helper roles poll with the suspend-time hint, 8 = L2 prefetch of the next Q,
-// 32 = the exponential loop is software-pipelined in the source (the MUFUs of chunk c+1 are issued before chunk c is packed),
-// 64 = two-pass S: the scores are read from TMEM once for the row maximum and again, 16 columns at a time, inside the
-//      exponential phase (32 instead of 64 live score registers there; S is released at the end of the phase)
-template <int D, int BKV, int ST, int VAR>
-__global__ void __launch_bounds__(640, 1) attention3_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
-  using Cfg = Attn3Cfg<D, BKV, ST>;
+template <int D, int BKV, int ST, int TPR>
+__global__ void __launch_bounds__(128 + 256 * TPR, 1) attention3_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
+  using Cfg = Attn3Cfg<D, BKV, ST, TPR>;
   constexpr int DK = Cfg::DK, DKL = Cfg::DKL, NCH = Cfg::NCH;
+  constexpr int NSW = 4 * TPR;        // softmax warps per group
+  constexpr int NTOK = 2 * 128 * TPR;  // threads on an XU-token barrier (both groups)
   extern __shared__ __align__(1024) uint8_t smem[];  // 128B-swizzled tiles need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;
@@ -87,10 +95,6 @@ __global__ void __launch_bounds__(640, 1) attention3_kernel(const __grid_constan
   uint64_t* o_free = o_full + 4;    // [q]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
-  auto hwait = [](uint64_t* bar, uint32_t parity) {
-    if constexpr ((VAR & 4) != 0) mbar_wait_relaxed(bar, parity);
-    else mbar_wait(bar, parity);
-  };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkv = (p.Tk + BKV - 1) / BKV;
   const int nqb = (p.Tq + 255) / 256;
@@ -115,12 +119,12 @@ __global__ void __launch_bounds__(640, 1) attention3_kernel(const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 8);
-      mbar_init(&p_full[2 * i], 8);
-      mbar_init(&p_full[2 * i + 1], 8);
+      mbar_init(&s_free[i], NSW);
+      mbar_init(&p_full[2 * i], NSW);
+      mbar_init(&p_full[2 * i + 1], NSW);
       mbar_init(&o_full[2 * i], 1);
       mbar_init(&o_full[2 * i + 1], 1);
-      mbar_init(&o_free[i], 8);
+      mbar_init(&o_free[i], NSW);
     }
     fence_barrier_init();
     tma_prefetch_desc(&maps.q);
@@ -145,27 +149,19 @@ __global__ void __launch_bounds__(640, 1) attention3_kernel(const __grid_constan
         int q0, head, b;
         decode(w, q0, head, b);
         const int kvb = p.kv_index ? p.kv_index[b] : b;
-        if (lw > 0) hwait(q_free, (lw - 1) & 1);  // every QK^T of the previous work item has completed
+        if (lw > 0) mbar_wait(q_free, (lw - 1) & 1);  // every QK^T of the previous work item has completed
         mbar_arrive_expect_tx(q_full, 2 * Cfg::Q_TILE_BYTES);
         for (int qq = 0; qq < 2; ++qq)
           for (int c = 0; c < NCH; ++c)
             tma_load_4d(sQ + qq * Cfg::Q_TILE_BYTES + c * 16384, &maps.q, q_full, c * 64, head, q0 + qq * 128, b);
-        if constexpr ((VAR & 8) != 0) {
-          if (w + static_cast<int>(gridDim.x) < total) {  // pull the next work item's Q into L2 long before it is needed
-            int q0n, headn, bn;
-            decode(w + gridDim.x, q0n, headn, bn);
-            for (int qq = 0; qq < 2; ++qq)
-              for (int c = 0; c < NCH; ++c) tma_prefetch_l2_4d(&maps.q, c * 64, headn, q0n + qq * 128, bn);
-          }
-        }
         for (int j = 0; j < nkv; ++j, ++g) {
           const int st = g % ST;
           const uint32_t ph = (g / ST) & 1;
-          hwait(&k_empty[st], ph ^ 1);
+          mbar_wait(&k_empty[st], ph ^ 1);
           mbar_arrive_expect_tx(&k_full[st], Cfg::K_BYTES);
           for (int c = 0; c < NCH; ++c)
             tma_load_4d(sK + st * Cfg::K_BYTES + c * BKV * 128, &maps.k, &k_full[st], c * 64, head, j * BKV, kvb);
-          hwait(&v_empty[st], ph ^ 1);
+          mbar_wait(&v_empty[st], ph ^ 1);
           mbar_arrive_expect_tx(&v_full[st], Cfg::V_BYTES);
           for (int c = 0; c < Cfg::NCHV; ++c)
             tma_load_4d(sV + st * Cfg::V_BYTES + c * BKV * 128, &maps.v, &v_full[st], c * 64, head, j * BKV, kvb);
@@ -200,9 +196,9 @@ __global__ void __launch_bounds__(640, 1) attention3_kernel(const __grid_constan
       int G = 0;  // tiles processed so far by this issuer (runs across work items: barrier parities follow it)
       int lw = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++lw) {
-        hwait(q_full, lw & 1);
-        hwait(&k_full[G % ST], (G / ST) & 1);
-        if (G > 0) hwait(&s_free[q], (G - 1) & 1);  // the softmax group holds S_q of the previous tile in registers
+        mbar_wait(q_full, lw & 1);
+        mbar_wait(&k_full[G % ST], (G / ST) & 1);
+        if (G > 0) mbar_wait(&s_free[q], (G - 1) & 1);  // the softmax group holds S_q of the previous tile in registers
         tc_fence_after();
         issue_qk(G % ST);
         umma_commit(&s_full[q]);
@@ -212,8 +208,8 @@ __global__ void __launch_bounds__(640, 1) attention3_kernel(const __grid_constan
           const uint32_t gp = G & 1;
           if (j + 1 < nkv) {
             const int st1 = (G + 1) % ST;
-            hwait(&k_full[st1], ((G + 1) / ST) & 1);
-            hwait(&s_free[q], gp);
+            mbar_wait(&k_full[st1], ((G + 1) / ST) & 1);
+            mbar_wait(&s_free[q], gp);
             tc_fence_after();
             issue_qk(st1);
             umma_commit(&s_full[q]);
@@ -221,9 +217,9 @@ __global__ void __launch_bounds__(640, 1) attention3_kernel(const __grid_constan
             if (j + 2 == nkv) umma_commit(q_free);  // last QK^T of this work item: Q may be overwritten once it completes
           }
           const int st = G % ST;
-          hwait(&v_ready[st], (G / ST) & 1);  // V tile landed and its ones column written
-          hwait(&p_full[2 * q + gp], (G >> 1) & 1);  // P_q in smem buffer G&1, O_q rescaled
-          if (j == 0 && lw > 0) hwait(&o_free[q], (lw - 1) & 1);  // the epilogue of the previous work item has read O_q
+          mbar_wait(&v_ready[st], (G / ST) & 1);            // V tile landed and its ones column written
+          mbar_wait(&p_full[2 * q + gp], (G >> 1) & 1);      // P_q in smem buffer G&1, O_q rescaled
+          if (j == 0 && lw > 0) mbar_wait(&o_free[q], (lw - 1) & 1);  // the epilogue of the previous work item has read O_q
           tc_fence_after();
           issue_pv(st, gp, j == 0);
           umma_commit(&o_full[2 * q + gp]);
@@ -237,7 +233,7 @@ __global__ void __launch_bounds__(640, 1) attention3_kernel(const __grid_constan
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       for (int j = 0; j < nkv; ++j, ++g) {
         const int st = g % ST;
-        hwait(&v_full[st], (g / ST) & 1);
+        mbar_wait(&v_full[st], (g / ST) & 1);
         uint8_t* vt = sV + st * Cfg::V_BYTES + Cfg::ONE_CHUNK * BKV * 128;
         for (int k = lane; k < BKV; k += 32)
           *reinterpret_cast<uint16_t*>(vt + k * 128 + ((Cfg::ONE_PIECE ^ (k & 7)) << 4) + Cfg::ONE_BYTE) = 0x3C00u;  // fp16 1.0
@@ -249,90 +245,69 @@ __global__ void __launch_bounds__(640, 1) attention3_kernel(const __grid_constan
   } else {
     // ============================== softmax groups ==============================
     constexpr int HC = Cfg::HC;
-    const int wg = (warp - 4) >> 3;
-    const int half = ((warp - 4) >> 2) & 1;  // which half of the key columns of the tile
-    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int wg = (warp - 4) / NSW;
+    const int half = TPR == 2 ? ((warp - 4) >> 2) & 1 : 0;  // which half of the key columns of the tile (TPR = 2)
+    const int quarter = warp & 3;                            // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
-    const int bar_id = 2 + wg;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t t_s = t_lane + wg * BKV + half * HC;
     const uint32_t t_o = t_lane + Cfg::O_COL + wg * DKL;
-    // P row of this thread: 128-byte swizzled rows; 16-byte piece i of 64-column chunk `half` sits at pbase ^ (i << 4)
-    const uint32_t p_row = smem_u32(sP) + 2 * wg * Cfg::P_TILE_BYTES + row * 128 + ((row & 7) << 4);
+    // P row of this thread: 128-byte swizzled rows inside 64-column chunks of 16 KB; 16-byte piece i of a chunk sits at
+    // (row base | (row & 7) << 4) ^ (i << 4).  The thread's first column is half * HC.
+    const uint32_t p_row = (smem_u32(sP) + 2 * wg * Cfg::P_TILE_BYTES + row * 128 + ((row & 7) << 4) + ((half * HC) >> 6) * 16384) ^
+                           (static_cast<uint32_t>(((half * HC) & 63) >> 3) << 4);
     uint64_t* o_full_q = o_full + 2 * wg;
     uint16_t* xg = xch + wg * 2 * 128 * 2 + row * 2;  // [parity][row][half]
     const float sc = p.scale_log2;
     const float thr = 8.f / sc;  // lazy rescale threshold in raw-score units (2^8 headroom)
     const uint64_t sc2 = pack_f2(sc, sc);
-    // O columns (in 16-column TMEM chunks, the l column included) this thread rescales on the rare path
-    constexpr int NCH16 = DKL / 16;
-    const int ch_lo = half == 0 ? 0 : (NCH16 + 1) / 2, ch_hi = half == 0 ? (NCH16 + 1) / 2 : NCH16;
-    constexpr int N8 = D / 8;
-    const int c8_lo = half == 0 ? 0 : (N8 + 1) / 2, c8_hi = half == 0 ? (N8 + 1) / 2 : N8;
+    // O columns (in 16-column TMEM chunks, the l column included) this thread rescales on the rare path, and the 8-column
+    // output pieces it stores in the epilogue (split between the two threads of a row when TPR = 2)
+    constexpr int NCH16 = DKL / 16, N8 = D / 8;
+    const int ch_lo = (TPR == 2 && half) ? (NCH16 + 1) / 2 : 0, ch_hi = (TPR == 2 && !half) ? (NCH16 + 1) / 2 : NCH16;
+    const int c8_lo = (TPR == 2 && half) ? (N8 + 1) / 2 : 0, c8_hi = (TPR == 2 && !half) ? (N8 + 1) / 2 : N8;
 
     int G = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       int q0, head, b;
       decode(w, q0, head, b);
       float m_ref = -INFINITY;
-      if constexpr ((VAR & 2) == 0) {
-        if (wg == 1) asm volatile("bar.arrive 4, 512;" ::: "memory");  // group 0 exponentiates first
-      }
+      if (wg == 1) nbar_arrive<4, NTOK>();  // group 0 exponentiates first
       for (int j = 0; j < nkv; ++j, ++G) {
         const uint32_t gp = G & 1;
         mbar_wait(&s_full[wg], gp);
         tc_fence_after();
+        uint32_t raw[HC];
+#pragma unroll
+        for (int c0 = 0; c0 < HC; c0 += 32) tmem_ld_x32(t_s + c0, raw + c0);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[wg]);
+
         const int kbase = j * BKV + half * HC;
-        const bool ragged = kbase + HC > p.Tk;  // ragged last tile
-        uint32_t raw[(VAR & 64) ? 1 : HC];
-        float mx0, mx1;
-        if constexpr ((VAR & 64) != 0) {
-          // pass 1: row maximum only, 32 columns at a time; S stays in tensor memory for the exponential phase
-          mx0 = -INFINITY;
-          mx1 = -INFINITY;
+        if (kbase + HC > p.Tk) {  // ragged last tile
 #pragma unroll
-          for (int c0 = 0; c0 < HC; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld_x32(t_s + c0, r);
-            tmem_wait_ld();
-            if (ragged) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (kbase + c0 + i >= p.Tk) r[i] = 0xff800000u;
-            }
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              mx0 = fmax3(mx0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-              mx1 = fmax3(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-            }
-          }
-        } else {
-#pragma unroll
-          for (int c0 = 0; c0 < HC; c0 += 32) tmem_ld_x32(t_s + c0, raw + c0);
-          tmem_wait_ld();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free[wg]);
-          if (ragged) {
-#pragma unroll
-            for (int i = 0; i < HC; ++i)
-              if (kbase + i >= p.Tk) raw[i] = 0xff800000u;  // -inf
-          }
-          mx0 = __uint_as_float(raw[0]);
-          mx1 = __uint_as_float(raw[1]);
-#pragma unroll
-          for (int i = 2; i < HC; i += 4) {
-            mx0 = fmax3(mx0, __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
-            if (i + 2 < HC) mx1 = fmax3(mx1, __uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]));
-          }
+          for (int i = 0; i < HC; ++i)
+            if (kbase + i >= p.Tk) raw[i] = 0xff800000u;  // -inf
         }
-        // the row's other half lives in the partner thread (warp + 4): both publish their half-row maximum rounded up to
-        // bf16 and take the larger one, so the two threads always agree on the reference maximum
-        const uint32_t mine = bf16_round_up_bits(fmaxf(mx0, mx1));
-        xg[gp * 256 + half] = static_cast<uint16_t>(mine);
-        named_bar_sync256(bar_id);
-        const uint32_t peer = xg[gp * 256 + (half ^ 1)];
-        const float mx = fmaxf(__uint_as_float(mine << 16), __uint_as_float(peer << 16));
+        float mx0 = __uint_as_float(raw[0]), mx1 = __uint_as_float(raw[1]);
+#pragma unroll
+        for (int i = 2; i < HC; i += 4) {
+          mx0 = fmax3(mx0, __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+          if (i + 2 < HC) mx1 = fmax3(mx1, __uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]));
+        }
+        float mx = fmaxf(mx0, mx1);
+        if constexpr (TPR == 2) {
+          // the row's other half lives in the partner thread (warp + 4): both publish their half-row maximum rounded up to
+          // bf16 and take the larger one, so the two threads always agree on the reference maximum
+          const uint32_t mine = bf16_round_up_bits(mx);
+          xg[gp * 256 + half] = static_cast<uint16_t>(mine);
+          if (wg == 0) nbar_sync<2, 256>();
+          else nbar_sync<3, 256>();
+          const uint32_t peer = xg[gp * 256 + (half ^ 1)];
+          mx = fmaxf(__uint_as_float(mine << 16), __uint_as_float(peer << 16));
+        }
         const bool grow = mx > m_ref + thr;  // true on the first tile (m_ref = -inf); identical in both halves
         const float alpha = grow ? exp2f((m_ref - mx) * sc) : 1.f;
         if (j > 0 && __any_sync(0xffffffffu, grow)) {
@@ -352,112 +327,40 @@ __global__ void __launch_bounds__(640, 1) attention3_kernel(const __grid_constan
         m_ref = grow ? mx : m_ref;
         // P buffer G&1 was last read by PV(G-2).  No wait is needed: this thread observed s_full(G), i.e. the completion
         // of QK(G), and tcgen05.commit tracks ALL earlier MMAs of the issuing thread -- PV(G-2) was issued before QK(G).
-        // ping-pong: the MUFU-bound exponential phases of the two groups alternate (token = named barrier 4 + group)
-        if constexpr ((VAR & 2) == 0) {
-          if (wg == 0) asm volatile("bar.sync 4, 512;" ::: "memory");
-          else asm volatile("bar.sync 5, 512;" ::: "memory");
-        }
+        // ping-pong: the MUFU-bound exponential phases of the two groups alternate (token = named barrier 4 + group);
+        // measured: without the token -19 %, handing it over early -3 %; evaluating 2 or 3 of every 8 exponentials with a
+        // degree-3 polynomial on the FMA pipe: +-0 % / -6 %
+        if (wg == 0) nbar_sync<4, NTOK>();
+        else nbar_sync<5, NTOK>();
         const float nmoff = -m_ref * sc;
         const uint64_t off2 = pack_f2(nmoff, nmoff);
-        // BKV = 128: the thread's 64 columns are 64-column chunk `half`; BKV = 64: pieces half*4 .. half*4+3 of the one chunk
-        const uint32_t pbase = (p_row + gp * Cfg::P_TILE_BYTES + (BKV == 128 ? half * 16384 : 0)) ^ (BKV == 128 ? 0u : static_cast<uint32_t>(half) << 6);
-        auto pass_token = [&]() {
-          // hand the XU token to the other group (group 1 keeps its last one: group 0 has no tile left to wait for)
-          if constexpr ((VAR & 2) == 0) {
-            if (wg == 0) asm volatile("bar.arrive 5, 512;" ::: "memory");
-            else if (j + 1 < nkv) asm volatile("bar.arrive 4, 512;" ::: "memory");
-          }
-        };
-        auto ex8 = [&](int c0, float* o) {
+        const uint32_t pbase = p_row + gp * Cfg::P_TILE_BYTES;
+#pragma unroll
+        for (int c0 = 0; c0 < HC; c0 += 8) {
+          uint32_t pk[4];
 #pragma unroll
           for (int i = 0; i < 8; i += 2) {
             const uint64_t x =
                 fma_f2(pack_f2(__uint_as_float(raw[c0 + i]), __uint_as_float(raw[c0 + i + 1])), sc2, off2);
             float e0, e1;
             unpack_f2(x, e0, e1);
-            o[i] = fast_exp2(e0);
-            o[i + 1] = fast_exp2(e1);
+            pk[i >> 1] = pack_h2(fast_exp2(e0), fast_exp2(e1));
           }
-        };
-        auto st8 = [&](int c0, const float* v) {
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pbase ^ static_cast<uint32_t>((c0 >> 3) << 4)),
-                       "r"(pack_h2(v[0], v[1])), "r"(pack_h2(v[2], v[3])), "r"(pack_h2(v[4], v[5])), "r"(pack_h2(v[6], v[7]))
+          // column c0 of this thread -> chunk (c0 >> 6), piece ((c0 & 63) >> 3) relative to the thread's first column
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"((pbase + (c0 >> 6) * 16384) ^ static_cast<uint32_t>(((c0 & 63) >> 3) << 4)),
+                       "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
                        : "memory");
-        };
-        if constexpr ((VAR & 64) != 0) {
-          // pass 2: 16 score columns at a time, the next block's TMEM load in flight under the exponentials of this one
-          constexpr int BW = 16, NB = HC / BW;
-          uint32_t blk[2][BW];
-          auto ex8r = [&](const uint32_t* r, float* o) {
-#pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-              const uint64_t x = fma_f2(pack_f2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc2, off2);
-              float e0, e1;
-              unpack_f2(x, e0, e1);
-              o[i] = fast_exp2(e0);
-              o[i + 1] = fast_exp2(e1);
-            }
-          };
-          tmem_ld_x16(t_s, blk[0]);
-          tmem_wait_ld();
-#pragma unroll
-          for (int nb = 0; nb < NB; ++nb) {
-            uint32_t* cur = blk[nb & 1];
-            if (nb + 1 < NB) tmem_ld_x16(t_s + (nb + 1) * BW, blk[(nb + 1) & 1]);
-            if (ragged) {
-#pragma unroll
-              for (int i = 0; i < BW; ++i)
-                if (kbase + nb * BW + i >= p.Tk) cur[i] = 0xff800000u;
-            }
-            float e[8], f[8];
-            ex8r(cur, e);
-            ex8r(cur + 8, f);
-            st8(nb * BW, e);
-            st8(nb * BW + 8, f);
-            if (nb + 1 < NB) {
-              tmem_wait_ld();
-              if (nb + 2 == NB) {  // the last block of S is in registers: QK^T of the next tile may overwrite it
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_free[wg]);
-              }
-            }
-          }
-          if constexpr (NB == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free[wg]);
-          }
-        } else if constexpr ((VAR & 32) != 0) {
-          float ea[8], eb[8];
-          ex8(0, ea);
-#pragma unroll
-          for (int c0 = 8; c0 < HC; c0 += 16) {
-            ex8(c0, eb);
-            st8(c0 - 8, ea);
-            if (c0 + 8 < HC) ex8(c0 + 8, ea);
-            st8(c0, eb);
-          }
-          if constexpr ((HC / 8) % 2 == 1) st8(HC - 8, ea);
-        } else {
-#pragma unroll
-          for (int c0 = 0; c0 < HC; c0 += 8) {
-            if constexpr ((VAR & 1) != 0) {
-              if (c0 == HC - 16) pass_token();  // the other group's start-up overlaps the tail of this exponential phase
-            }
-            float e[8];
-            ex8(c0, e);
-            st8(c0, e);
-          }
         }
-        if constexpr ((VAR & 1) == 0) pass_token();
+        // hand the XU token to the other group (group 1 keeps its last one: group 0 has no tile left to wait for)
+        if (wg == 0) nbar_arrive<5, NTOK>();
+        else if (j + 1 < nkv) nbar_arrive<4, NTOK>();
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[2 * wg + gp]);
       }
 
-      // ---- epilogue of the work item: O / l -> fp16; the two threads of a row split the head dim; l = TMEM column D
+      // ---- epilogue of the work item: O / l -> fp16; l = TMEM column D (accumulated by the PV MMA from the ones column)
       const int Gl = G - 1;  // last tile of this work item
       mbar_wait(&o_full_q[Gl & 1], (Gl >> 1) & 1);
       tc_fence_after();

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 
 #include "misc.cuh"
 #include "norm.cuh"
@@ -369,19 +370,16 @@ static void attn2_launch_d(const AttnOp& op, cudaStream_t s) {
   attention2_kernel<D, BKV, ST><<<op.grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
   DM_CUDA(cudaGetLastError());
 }
-template <int D, int BKV, int ST, int VAR>
+template <int D, int BKV, int ST, int TPR>
 static void attn3_launch_d(const AttnOp& op, cudaStream_t s) {
   static bool configured[64] = {};
-  using Cfg = Attn3Cfg<D, BKV, ST>;
+  using Cfg = Attn3Cfg<D, BKV, ST, TPR>;
   if (first_use_on_this_device(configured)) {
-    DM_CUDA(cudaFuncSetAttribute(attention3_kernel<D, BKV, ST, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    DM_CUDA(cudaFuncSetAttribute(attention3_kernel<D, BKV, ST, TPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   }
-  attention3_kernel<D, BKV, ST, VAR><<<op.grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
+  attention3_kernel<D, BKV, ST, TPR><<<op.grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
   DM_CUDA(cudaGetLastError());
 }
-#ifndef DM_ATTN3_VAR
-#define DM_ATTN3_VAR 0
-#endif
 template <int D>
 static void xattn_launch_d(const AttnOp& op, cudaStream_t s) {
   static bool configured[64] = {};
@@ -415,26 +413,11 @@ void attn_launch(const AttnOp& op, cudaStream_t s) {
     return;
   }
   if (op.v3) {
-#ifdef DM_ATTN3_EXPERIMENT
-    // tuning build: attn3 = 1 + VAR selects the variant at run time (tools/ab.py attn)
-    const int var = variant_attn3() - 1;
-    if (op.D == 40) {
-      switch (var) {
-        case 32: attn3_launch_d<40, 128, 2, 32>(op, s); break;
-        case 64: attn3_launch_d<40, 128, 2, 64>(op, s); break;
-        default: attn3_launch_d<40, 128, 2, 0>(op, s); break;
-      }
-    } else {
-      switch (var) {
-        case 32: attn3_launch_d<80, 64, 3, 32>(op, s); break;
-        case 64: attn3_launch_d<80, 64, 3, 64>(op, s); break;
-        default: attn3_launch_d<80, 64, 3, 0>(op, s); break;
-      }
-    }
-    return;
-#endif
-    if (op.D == 40) attn3_launch_d<40, 128, 2, DM_ATTN3_VAR>(op, s);
-    else attn3_launch_d<80, 64, 3, DM_ATTN3_VAR>(op, s);
+    // attn3 = 1: two softmax threads per query row (16 softmax warps, default); attn3 = 2: one thread per row (8 softmax
+    // warps, 168 registers): equal at head_dim 80, 14 % slower at head_dim 40 (gpurun_out/r02_ab_attn5.log)
+    const bool one = variant_attn3() == 2;
+    if (op.D == 40) one ? attn3_launch_d<40, 128, 2, 1>(op, s) : attn3_launch_d<40, 128, 2, 2>(op, s);
+    else one ? attn3_launch_d<80, 64, 3, 1>(op, s) : attn3_launch_d<80, 64, 3, 2>(op, s);
     return;
   }
   if (op.v2) {

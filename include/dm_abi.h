@@ -147,7 +147,8 @@ int dm_op_layernorm(const void* x, int64_t rows, int C, const float* gamma, cons
  *   igemm_ng4   1 = four epilogue warpgroups for short-K (epilogue-bound) layers, 0 = always two, 2 = wherever possible
  *   gn_fused    1 = cluster-fused single-pass GroupNorm for images that fit in L2, 0 = two-kernel path
  *   xattn       1 = short-key-set cross-attention kernel (P in tensor memory), 0 = generic flash kernel
- *   attn3       1 = persistent self-attention kernel (attention3.cuh), 0 = one CTA per 256-query block (attention2.cuh)
+ *   attn3       persistent self-attention kernel (attention3.cuh): 1 = two softmax threads per query row, 2 = one thread per
+ *               row; 0 = one CTA per 256-query block (attention2.cuh)
  *   prefix_share 1 = dm_typicality computes the context-free U-Net prefix once per (eps,t) draw (bit-identical) */
 int dm_op_set_variant(const char* name, int value);
 

@@ -192,10 +192,10 @@ def test_flash_attention(lib, case):
 
 @pytest.mark.parametrize("case", [c for c in ATTN_CASES if not c[4] and c[3] in (40, 80)] + [(20, 1024, 1024, 40, 0), (40, 300, 300, 80, 0)],
                          ids=lambda c: "-".join(map(str, c)))
-def test_flash_attention_non_persistent_variant(lib, case):
-    """the one-CTA-per-query-block kernel (attention2) stays available behind the `attn3` switch; the default is the
-    persistent kernel (attention3), exercised by test_flash_attention -- the extra cases give a CTA several work items"""
-    for v in (0, 1):
+def test_flash_attention_variants(lib, case):
+    """`attn3` switch: 0 = one CTA per query block (attention2), 1 = persistent kernel with two softmax threads per query
+    row, 2 = persistent kernel with one thread per row; the extra cases give a persistent CTA several work items"""
+    for v in (0, 1, 2):
         check(lib, lib.dm_op_set_variant(b"attn3", v))
         try:
             test_flash_attention(lib, case)

@@ -94,7 +94,7 @@ def stress():
         args = (ptr(qkv[..., :C]), ptr(qkv[..., C:2 * C]), ptr(qkv[..., 2 * C:]), 3 * C, 3 * C, 3 * C, T * 3 * C, T * 3 * C, T * 3 * C, B, 8, D, T, T, 0,
                 None, ptr(out), C, stream())
         junk = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
-        for v_ in (1, 0):
+        for v_ in (2, 1, 0):
             o.check(lib.dm_op_set_variant(b"attn3", v_))
             o.check(lib.dm_op_attention(*args))
             torch.cuda.synchronize()

@@ -10,7 +10,7 @@ import torch
 import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = ctypes.CDLL(os.path.join(ROOT, "diff-mining_b200", "libdm_b200.so"))
+lib = ctypes.CDLL(os.environ.get("DM_LIB") or os.path.join(ROOT, "diff-mining_b200", "libdm_b200.so"))
 lib.dm_last_error.restype = ctypes.c_char_p
 P = ctypes.c_void_p
 I = ctypes.c_int
