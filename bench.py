@@ -574,7 +574,7 @@ def run_ours(args):
         ach = pr["flops_igemm"] / (pr["ms_igemm"] * 1e-3) / 1e12
         att = pr["flops_attn"] / (pr["ms_attn"] * 1e-3) / 1e12
         line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                            "traffic": load_traffic(f"config{args.config}", Bf, aux),
+                            "traffic": load_traffic(f"config{2 if args.config == 4 else args.config}", Bf, aux),  # config 4 replays config 2's plan
                             "kernel": "dm::igemm_kernel<BN> (tcgen05 implicit GEMM: all convs + Linears)",
                             "plan": {"kind": kind, "Bf": Bf, "h": h, "w": w, "aux": aux},
                             "peak_source": pk["source"],
