@@ -41,6 +41,7 @@ SIGNATURES = {
     "dm_profile_unet": (I, [P, I, I, I, I, PD, PD, PD, PD, PD]),
     "dm_profile_plan": (I, [P, I, I, I, I, I, I, PD, PD]),
     "dm_op_conv": (I, [P, P, I, I, I, I, I, P, I, I, I, I, P, P, P, P, I, I, I, I, P]),
+    "dm_op_conv_gn": (I, [P, I, I, I, I, P, I, I, P, P, P, P, P, F, I, P, P, P]),
     "dm_op_attention": (I, [P, P, P, L, L, L, L, L, L, I, I, I, I, I, I, P, P, L, P]),
     "dm_op_groupnorm": (I, [P, P, I, I, I, I, P, P, F, I, P, P]),
     "dm_op_layernorm": (I, [P, L, I, P, P, F, P, P]),

@@ -77,6 +77,47 @@ extern "C" int dm_op_conv(const void* x, const void* x2, int N, int H, int W, in
   });
 }
 
+extern "C" int dm_op_conv_gn(const void* x, int N, int H, int W, int C0, const void* w, int Cout, int ks, const float* bias,
+                             const void* rowbias, const void* residual, const float* gamma, const float* beta, float eps,
+                             int silu, void* out, void* gn_out, void* stream) {
+  return abi_guard([&] {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DM_CHECK(ks == 1 || ks == 3, "conv_gn: kernel size must be 1 or 3");
+    DM_CHECK(C0 % 64 == 0 && Cout % 64 == 0 && Cout <= 1280, "conv_gn: channels must be multiples of 64, Cout <= 1280");
+    DM_CHECK(igemm_gn_fusable(H, W, Cout) && gn_fold_apply_supported(H * W, Cout, 0),
+             "conv_gn: this shape cannot form GroupNorm statistics in the conv epilogue");
+    IgemmDesc d;
+    d.src[0] = ActView{static_cast<const __half*>(x), N, H, W, C0, C0};
+    d.nsrc = 1;
+    if (ks == 3) seg_conv3x3(d, C0, C0);
+    else seg_1x1(d, C0, 0);
+    d.Nimg = N; d.H = H; d.W = W;
+    d.Wt = static_cast<const __half*>(w);
+    d.N = Cout;
+    d.K = ks * ks * C0;
+    d.bias = bias;
+    d.rowbias = static_cast<const __half*>(rowbias);
+    d.ld_rowbias = Cout;
+    d.residual = static_cast<const __half*>(residual);
+    d.ld_res = Cout;
+    d.out = out;
+    d.ld_out = Cout;
+    float* rec = nullptr;
+    DM_CUDA(cudaMalloc(&rec, sizeof(float) * gn_record_floats(N, H * W, Cout)));
+    float* scratch = rec;
+    d.gn.rec = rec;
+    IgemmOp op = igemm_prepare(d, device_sm_count());
+    igemm_launch(op, s);
+    GnDesc g;
+    g.src0 = static_cast<const __half*>(out); g.C0 = Cout; g.ps0 = Cout;
+    g.Nimg = N; g.HW = H * W; g.gamma = gamma; g.beta = beta; g.eps = eps; g.silu = silu;
+    g.out = static_cast<__half*>(gn_out);
+    gn_fold_apply_launch(g, rec, nullptr, s);
+    DM_CUDA(cudaStreamSynchronize(s));
+    DM_CUDA(cudaFree(scratch));
+  });
+}
+
 extern "C" int dm_op_attention(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_k, int64_t ld_v,
                                int64_t bs_q, int64_t bs_k, int64_t bs_v, int B, int heads, int D, int Tq, int Tk,
                                int kv_batches, const int32_t* kv_index_dev, void* out, int64_t ld_out, void* stream) {

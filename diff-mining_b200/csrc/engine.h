@@ -43,6 +43,9 @@ struct Act {  // NHWC fp16 activation inside a plan's arena
   size_t off = 0;
   int N = 0, H = 0, W = 0, C = 0;
   bool valid = false;
+  // GroupNorm statistics record left by the producing conv's epilogue (igemm.cuh: IgGn), in the arena next to the data
+  size_t st_off = 0;
+  bool stats = false;
   long long pixels() const { return static_cast<long long>(N) * H * W; }
   size_t bytes() const { return static_cast<size_t>(pixels()) * C * sizeof(__half); }
 };

@@ -55,6 +55,21 @@ struct IgLossArgs {
   __half* grid_f16;        // [rows, 4, H, W] fp16; null = epilogue disabled for this replay
 };
 
+// GroupNorm statistics of the OUTPUT tensor, formed in the producing conv's epilogue (the following GroupNorm then only has
+// to fold them and apply y = x * a + b: reference op order conv1 -> +temb -> norm2 -> SiLU,
+// applications/parallel-dataset/pnp.py:318-345).  After a chunk (128 rows x 32 columns of final fp16 values) is staged in
+// shared memory for its TMA store, the 128 threads of the epilogue group re-read it COLUMN-wise (thread = column pair x
+// 16 alternate rows of its warp's 32; conflict-free on the 64-byte-swizzled chunk) and store the per-column shifted sums
+// S = sum(x - k), Q = sum((x - k)^2) per (image, m-tile, warp quarter, channel); k = bias + time-embedding bias + the
+// residual's value at the image's first pixel (known to every tile of the image, so the sums are additive) is written once
+// per (image, channel) by the image's first tile.  No atomics, no completion protocol: gn_fold_apply_kernel folds the
+// partials in a fixed order.  Requires whole 128-pixel tiles per image (conv layout: nt_log == 0; flattened Linear layout:
+// H * W % 128 == 0) and N a multiple of the N-tile.
+struct IgGn {
+  float* rec;           // per image: [E = tiles_img * 4][N][2] (S, Q) partials, then [N] shifts k -- (2E + 1) * N floats
+  int tiles_img;        // m-tiles per image (m-tile mt belongs to image mt / tiles_img)
+};
+
 struct IgParams {
   int Nimg, H, W;                 // OUTPUT pixel grid; M = Nimg*H*W
   int wt_log, ht_log, nt_log;     // M-tile = 2^nt images x 2^ht rows x 2^wt cols (=128 pixels)
@@ -72,6 +87,7 @@ struct IgParams {
   long long ld_out;
   int out_f32, geglu, act_silu;
   const IgLossArgs* loss;         // direct epilogue only: fused (pred - eps)^2 -> fp16 grid (null = off)
+  IgGn gn;                        // staged epilogue only: GroupNorm statistics of the output (gn.rec == null = off)
 };
 
 // CG = CTAs per tile: 1, or 2 = a CTA pair (cta_group::2) computing a 256 x BN tile with each CTA holding its 128
@@ -455,6 +471,25 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) igemm_kernel(const __grid_co
         for (int c = c_first; c < nchunk; c += NG, ++k) {
           const int b = k % NBG;
           uint8_t* buf = ring + b * IG_CHUNK_BYTES + row_off;
+          // fused GroupNorm statistics (see IgGn): this thread's two columns' shift, fetched ahead of its use
+          float k0 = 0.f, k1 = 0.f;
+          int n_img = 0, t_img = 0;
+          if (p.gn.rec != nullptr && mt < p.m_tiles) {
+            n_img = mt / p.gn.tiles_img;
+            t_img = mt % p.gn.tiles_img;
+            const int col = ntile * BN + c * IG_CW + 2 * (lane & 15);  // first of this thread's two output columns
+            if (p.bias) { k0 = sbias[c * 32 + 2 * (lane & 15)]; k1 = sbias[c * 32 + 2 * (lane & 15) + 1]; }
+            if (p.rowbias) {
+              const float2 a = __half22float2(__ldg(reinterpret_cast<const __half2*>(
+                  p.rowbias + static_cast<long long>(n_img) * p.ld_rowbias + col)));
+              k0 += a.x; k1 += a.y;
+            }
+            if (has_res) {  // the residual's value at the image's first pixel
+              const float2 a = __half22float2(__ldg(reinterpret_cast<const __half2*>(
+                  p.residual + static_cast<long long>(n_img) * p.gn.tiles_img * IG_BM * p.ld_res + col)));
+              k0 += a.x; k1 += a.y;
+            }
+          }
           uint32_t pk[16];  // 32 output halves
           if (p.geglu) {
             // 64 accumulator columns = (value, gate) x 32 outputs, drained in two 32-column TMEM reads
@@ -542,6 +577,35 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) igemm_kernel(const __grid_co
                          ty << p.ht_log, tn << p.nt_log);
             tma_store_commit();
             if (has_res) prefetch_one();
+          }
+          if (p.gn.rec != nullptr && mt < p.m_tiles) {
+            // GroupNorm statistics of the staged chunk (see IgGn).  Safe against the ring: this buffer is next written by
+            // a residual prefetch / a later chunk only after a later named barrier, which every thread reaches after
+            // these reads in program order.
+            const int cp = lane & 15, hrow = lane >> 4;
+            const int col = ntile * BN + c * IG_CW + 2 * cp;
+            const uint8_t* cb = ring + b * IG_CHUNK_BYTES + static_cast<uint32_t>(quarter * 32 + hrow) * 64u +
+                                static_cast<uint32_t>(cp & 3) * 4u;
+            const uint32_t unit16 = static_cast<uint32_t>(cp >> 2);
+            float S0 = 0.f, S1 = 0.f, Q0 = 0.f, Q1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {  // row quarter*32 + hrow + 2i: its swizzle term (row >> 1) & 3 is i & 3
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(cb + i * 128 + ((unit16 ^ static_cast<uint32_t>(i & 3)) << 4));
+              const float2 f = __half22float2(u2h(u));
+              const float d0 = f.x - k0, d1 = f.y - k1;
+              S0 += d0; S1 += d1;
+              Q0 = fmaf(d0, d0, Q0); Q1 = fmaf(d1, d1, Q1);
+            }
+            S0 += __shfl_xor_sync(0xffffffffu, S0, 16); S1 += __shfl_xor_sync(0xffffffffu, S1, 16);
+            Q0 += __shfl_xor_sync(0xffffffffu, Q0, 16); Q1 += __shfl_xor_sync(0xffffffffu, Q1, 16);
+            if (hrow == 0) {
+              const int E = p.gn.tiles_img * 4;
+              float* rec = p.gn.rec + static_cast<long long>(n_img) * (2 * E + 1) * p.N;
+              *reinterpret_cast<float4*>(rec + (static_cast<long long>(t_img * 4 + quarter) * p.N + col) * 2) =
+                  make_float4(S0, Q0, S1, Q1);
+              if (t_img == 0 && quarter == 0)
+                *reinterpret_cast<float2*>(rec + static_cast<long long>(2 * E) * p.N + col) = make_float2(k0, k1);
+            }
           }
         }
         if (c_first >= nchunk) {  // this group owns no chunk of the tile: still release the accumulator

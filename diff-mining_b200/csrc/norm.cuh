@@ -350,6 +350,146 @@ __global__ void __launch_bounds__(384, MINB) gn_fused_kernel(NormSrc s0, NormSrc
   for (; px < p1; px += R) apply(__ldcg(reinterpret_cast<const uint4*>(base + px * ps)), px);
 }
 
+// GroupNorm whose statistics were formed by the epilogues of the convs that produced its input(s) (IgGn, igemm.cuh): fold +
+// apply in ONE kernel, one cluster of CL (4, 8 or 16) CTAs per image; like the kernels above it normalises cat(src0, src1)
+// without materialising it.  grid (CL, Nimg), cluster (CL, 1, 1).
+//   first   every thread issues the first UNR 16-byte loads of its apply pass (they do not depend on the statistics), so
+//           the fold below runs in the shadow of their latency
+//   fold    CTA `rank` owns 32/CL groups (C/CL channels): thread (slice, channel) sums every NS-th entry of the source's
+//           record [E][C_src][2] in index order, the slices are added in index order, each group is reduced by one warp
+//           with a fixed xor tree (same shifted-sum algebra as above) -> (a, b) per channel, which the CTA writes into the
+//           shared memory of all CTAs of the image (distributed shared memory)
+//   cluster.sync (the only one)
+//   apply   CTA `rank` normalises (+SiLU) pixels [rank*px_per, (rank+1)*px_per): 1 read + 1 write of the activation.
+// Deterministic and batch-invariant: the entry order, slice count (a function of C) and trees are fixed.
+struct GnStatSrc {
+  const __half* x;   // dense [Nimg][HW][C]
+  const float* rec;  // per image [E][C][2] partial (S, Q), then [C] shifts
+  int C;
+};
+constexpr int GN_FOLD_MAXC = 2048;
+template <int THREADS, int MINB, int UNR>
+__global__ void __launch_bounds__(THREADS, MINB) gn_fold_apply_kernel(GnStatSrc s0, GnStatSrc s1, int HW, int cpg, int px_per,
+                                                                       int VT, int R, int E, const float* __restrict__ gamma,
+                                                                       const float* __restrict__ beta, float eps, int silu,
+                                                                       __half* __restrict__ out) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float2 ab_s[GN_FOLD_MAXC];  // (a, b) of every channel of the image, filled by the CTAs of the cluster
+  __shared__ float sl_s[THREADS], sl_q[THREADS];  // [slice][channel of this CTA]
+  __shared__ float ch_s[THREADS], ch_q[THREADS], ch_k[THREADS];
+  const int n = blockIdx.y;
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int CL = static_cast<int>(cluster.num_blocks());
+  const int tid = threadIdx.x;
+  const int C = s0.C + s1.C;
+  // ---- apply-pass thread map and its first batch of loads
+  const bool active = tid < VT * R;
+  const int r = tid / VT, vt = tid % VT;
+  const int c = vt << 3;
+  const int p0 = min(HW, rank * px_per), p1 = min(HW, p0 + px_per);
+  const bool in0 = c < s0.C;
+  const long long ps = in0 ? s0.C : s1.C;  // pixel stride of this thread's source
+  const __half* base = (in0 ? s0.x + c : s1.x + (c - s0.C)) + static_cast<long long>(n) * HW * ps;
+  uint4 u[UNR];
+  int px = p0 + r;
+  const bool first_full = active && px + (UNR - 1) * R < p1;
+  if (first_full) {
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(base + (px + k * R) * ps));
+  }
+  // ---- fold
+  const int nch = C / CL;        // channels folded by this CTA
+  const int c0 = rank * nch;
+  const int NS = THREADS / nch;  // entry slices (>= 1: the launcher keeps C / CL <= THREADS)
+  if (tid < NS * nch) {
+    const int sl = tid / nch, ch = tid % nch;
+    const int gc = c0 + ch;
+    const bool f0 = gc < s0.C;
+    const int Cs = f0 ? s0.C : s1.C, lc = f0 ? gc : gc - s0.C;
+    const float2* pp = reinterpret_cast<const float2*>((f0 ? s0.rec : s1.rec) + static_cast<long long>(n) * (2 * E + 1) * Cs) + lc;
+    float s = 0.f, q = 0.f;
+    int e = sl;
+    for (; e + 3 * NS < E; e += 4 * NS) {
+      const float2 v0 = __ldcg(pp + static_cast<long long>(e) * Cs), v1 = __ldcg(pp + static_cast<long long>(e + NS) * Cs);
+      const float2 v2 = __ldcg(pp + static_cast<long long>(e + 2 * NS) * Cs), v3 = __ldcg(pp + static_cast<long long>(e + 3 * NS) * Cs);
+      s += v0.x; q += v0.y; s += v1.x; q += v1.y; s += v2.x; q += v2.y; s += v3.x; q += v3.y;
+    }
+    for (; e < E; e += NS) {
+      const float2 v = __ldcg(pp + static_cast<long long>(e) * Cs);
+      s += v.x; q += v.y;
+    }
+    sl_s[tid] = s;
+    sl_q[tid] = q;
+  }
+  __syncthreads();
+  if (tid < nch) {
+    float s = 0.f, q = 0.f;
+    for (int i = 0; i < NS; ++i) { s += sl_s[i * nch + tid]; q += sl_q[i * nch + tid]; }
+    ch_s[tid] = s;
+    ch_q[tid] = q;
+    const int gc = c0 + tid;
+    const bool f0 = gc < s0.C;
+    const int Cs = f0 ? s0.C : s1.C, lc = f0 ? gc : gc - s0.C;
+    ch_k[tid] = __ldcg((f0 ? s0.rec : s1.rec) + static_cast<long long>(n) * (2 * E + 1) * Cs + static_cast<long long>(2 * E) * Cs + lc);
+  }
+  __syncthreads();
+  if (tid < 32 * (32 / CL)) {  // warp g: group (32/CL)*rank + g
+    const int g = tid >> 5, lane = tid & 31;
+    const float cnt = static_cast<float>(HW);
+    float gs = 0.f;
+    for (int cc = lane; cc < cpg; cc += 32) gs += ch_s[g * cpg + cc] + cnt * ch_k[g * cpg + cc];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
+    const float mean = gs / (cnt * cpg);
+    float m2 = 0.f;
+    for (int cc = lane; cc < cpg; cc += 32) {
+      const float d = mean - ch_k[g * cpg + cc];
+      m2 += ch_q[g * cpg + cc] - 2.f * d * ch_s[g * cpg + cc] + cnt * d * d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+    const float rstd = rsqrtf(fmaxf(m2 / (cnt * cpg), 0.f) + eps);
+    for (int cc = lane; cc < cpg; cc += 32) {
+      const int ch = c0 + g * cpg + cc;
+      const float sc = __ldg(gamma + ch) * rstd;
+      const float2 v = make_float2(sc, __ldg(beta + ch) - mean * sc);
+      for (int peer = 0; peer < CL; ++peer) cluster.map_shared_rank(ab_s, peer)[ch] = v;
+    }
+  }
+  cluster.sync();
+  if (!active) return;
+  // ---- apply
+  float sa[8], sb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sa[i] = ab_s[c + i].x; sb[i] = ab_s[c + i].y; }
+  __half* obase = out + static_cast<long long>(n) * HW * C + c;
+  auto apply = [&](const uint4& v, int pxl) {
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      float y0 = f.x * sa[2 * i] + sb[2 * i], y1 = f.y * sa[2 * i + 1] + sb[2 * i + 1];
+      if (silu) { y0 = silu_fast(y0); y1 = silu_fast(y1); }
+      pk[i] = pack_h2(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(obase + static_cast<long long>(pxl) * C) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  };
+  if (first_full) {
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) apply(u[k], px + k * R);
+    px += UNR * R;
+  }
+  for (; px + (UNR - 1) * R < p1; px += UNR * R) {
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(base + (px + k * R) * ps));
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) apply(u[k], px + k * R);
+  }
+  for (; px < p1; px += R) apply(__ldg(reinterpret_cast<const uint4*>(base + px * ps)), px);
+}
+
 // LayerNorm over the last dim (C <= 32*8*MAXV, multiple of 8).  Persistent warps: a warp walks rows
 // w, w+W, ... holding one row in registers while the next row's loads are already in flight.  The kernel is
 // FMA-pipe-bound, not HBM-bound (plain fp32 FMA-pipe instructions issue every other cycle), so all per-element math
@@ -468,6 +608,174 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) cur[k] = nxt[k];
     row = nrow;
+  }
+}
+
+// LayerNorm for C = 40 * LPR (320 / 640 / 1280: every Transformer2DModel width): LPR lanes per row, five 16-byte vectors per
+// lane, 32 / LPR rows per warp -- every lane loads, computes and stores (the generic kernel above leaves 37.5 % of a warp
+// idle at C = 320).  Persistent warps with the next rows' loads in flight, two-pass statistics in registers, xor-tree
+// reductions over the LPR lanes of a row (fixed order: deterministic).
+template <int LPR>
+__global__ void __launch_bounds__(256) layernorm5_kernel(const __half* __restrict__ x, long long ld_x,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         float eps, long long rows, __half* __restrict__ out,
+                                                         long long ld_out) {
+  constexpr int C = 40 * LPR, RPW = 32 / LPR;
+  extern __shared__ float sm_ln[];  // gamma[C] | beta[C]
+  float* sg = sm_ln;
+  float* sb = sm_ln + C;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    sg[i] = gamma[i];
+    sb[i] = beta[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, j = lane % LPR;
+  const long long stride = static_cast<long long>(gridDim.x) * (blockDim.x >> 5) * RPW;
+  long long row = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
+  uint4 cur[5], nxt[5];
+  auto load = [&](uint4* dst, long long rw) {
+    const __half* px = x + rw * ld_x + (j << 3);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) dst[k] = __ldg(reinterpret_cast<const uint4*>(px + k * LPR * 8));
+  };
+  if (row < rows) load(cur, row);
+  constexpr float invC = 1.f / static_cast<float>(C);
+  // rows of a warp run out together except in the last sweep: the shuffles below stay inside a row's own LPR lanes, and
+  // lanes whose row is past the end keep executing them on stale registers without storing
+  while (__any_sync(0xffffffffu, row < rows)) {
+    const bool live = row < rows;
+    const long long nrow = row + stride;
+    if (nrow < rows) load(nxt, nrow);
+    float v[5][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const __half2* h = reinterpret_cast<const __half2*>(&cur[k]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        v[k][2 * i] = f.x;
+        v[k][2 * i + 1] = f.y;
+        s += f.x + f.y;
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[k][i] -= mean;
+        q = fmaf(v[k][i], v[k][i], q);
+      }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * invC + eps);
+    if (live) {
+      __half* po = out + row * ld_out + (j << 3);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const float4* g4 = reinterpret_cast<const float4*>(sg + ((j + k * LPR) << 3));
+        const float4* b4 = reinterpret_cast<const float4*>(sb + ((j + k * LPR) << 3));
+        const float4 g0 = g4[0], g1 = g4[1], b0 = b4[0], b1 = b4[1];
+        const uint32_t p0 = pack_h2(fmaf(v[k][0] * rstd, g0.x, b0.x), fmaf(v[k][1] * rstd, g0.y, b0.y));
+        const uint32_t p1 = pack_h2(fmaf(v[k][2] * rstd, g0.z, b0.z), fmaf(v[k][3] * rstd, g0.w, b0.w));
+        const uint32_t p2 = pack_h2(fmaf(v[k][4] * rstd, g1.x, b1.x), fmaf(v[k][5] * rstd, g1.y, b1.y));
+        const uint32_t p3 = pack_h2(fmaf(v[k][6] * rstd, g1.z, b1.z), fmaf(v[k][7] * rstd, g1.w, b1.w));
+        *reinterpret_cast<uint4*>(po + k * LPR * 8) = make_uint4(p0, p1, p2, p3);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) cur[k] = nxt[k];
+    row = nrow;
+  }
+}
+
+// Same row map without the register prefetch: the row stays packed (20 registers), the three passes convert on the fly, and
+// the overlap comes from occupancy (4 CTAs = 32 warps per SM) instead of from a second row buffer.  gamma / beta sit in
+// shared memory as fp16 (they ARE fp16 weights in the engine; the fp32 copies the launcher receives convert back exactly),
+// gamma and beta of one 8-channel vector side by side: 32 bytes of shared-memory reads per 16-byte vector instead of 64 --
+// the kernel was L1/LSU-pipe-bound (84 % l1tex throughput, profiles/r02_norm_kernels.txt), not HBM-bound.
+template <int LPR, int MINB>
+__global__ void __launch_bounds__(256, MINB) layernorm5b_kernel(const __half* __restrict__ x, long long ld_x,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float eps, long long rows, __half* __restrict__ out,
+                                                                long long ld_out) {
+  constexpr int C = 40 * LPR, RPW = 32 / LPR;
+  __shared__ __align__(16) __half sgb[2 * C];  // per 8-channel vector: gamma[8] | beta[8]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    sgb[(i >> 3) * 16 + (i & 7)] = __float2half_rn(gamma[i]);
+    sgb[(i >> 3) * 16 + 8 + (i & 7)] = __float2half_rn(beta[i]);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, j = lane % LPR;
+  const long long stride = static_cast<long long>(gridDim.x) * (blockDim.x >> 5) * RPW;
+  constexpr float invC = 1.f / static_cast<float>(C);
+  for (long long row0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW; row0 < rows;
+       row0 += stride) {
+    const long long row = row0 + sub;
+    const bool live = row < rows;
+    uint4 cur[5];
+    if (live) {
+      const __half* px = x + row * ld_x + (j << 3);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) cur[k] = __ldg(reinterpret_cast<const uint4*>(px + k * LPR * 8));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) cur[k] = make_uint4(0, 0, 0, 0);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const __half2* h = reinterpret_cast<const __half2*>(&cur[k]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        s += f.x + f.y;
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const __half2* h = reinterpret_cast<const __half2*>(&cur[k]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        const float d0 = f.x - mean, d1 = f.y - mean;
+        q = fmaf(d0, d0, q);
+        q = fmaf(d1, d1, q);
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * invC + eps);
+    const float nmr = -mean * rstd;
+    if (live) {
+      __half* po = out + row * ld_out + (j << 3);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const __half2* h = reinterpret_cast<const __half2*>(&cur[k]);
+        const uint4 gv = *reinterpret_cast<const uint4*>(sgb + (j + k * LPR) * 16);
+        const uint4 bv = *reinterpret_cast<const uint4*>(sgb + (j + k * LPR) * 16 + 8);
+        const __half2* gh = reinterpret_cast<const __half2*>(&gv);
+        const __half2* bh = reinterpret_cast<const __half2*>(&bv);
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(h[i]), g = __half22float2(gh[i]), b = __half22float2(bh[i]);
+          // (x - mean) * rstd = x * rstd + (-mean * rstd), then * gamma + beta
+          pk[i] = pack_h2(fmaf(fmaf(f.x, rstd, nmr), g.x, b.x), fmaf(fmaf(f.y, rstd, nmr), g.y, b.y));
+        }
+        *reinterpret_cast<uint4*>(po + k * LPR * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
   }
 }
 

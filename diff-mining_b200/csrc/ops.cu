@@ -77,6 +77,8 @@ static int g_xattn = -1, g_prefix = -1, g_ng4 = -1, g_attn3 = -1;
 static int variant_attn3() { return g_attn3 >= 0 ? g_attn3 : env_or("DM_ATTN3", 1); }
 static int variant_igemm_ng4() { return g_ng4 >= 0 ? g_ng4 : env_or("DM_IGEMM_NG4", 1); }
 int variant_prefix_share() { return g_prefix >= 0 ? g_prefix : env_or("DM_PREFIX_SHARE", 1); }
+static int g_gn_epi = -1;
+int gn_epilogue_mode() { return g_gn_epi >= 0 ? g_gn_epi : env_or("DM_GN_EPILOGUE", 3); }
 static int variant_xattn() { return g_xattn >= 0 ? g_xattn : env_or("DM_XATTN", 1); }
 void set_variant(const std::string& name, int value) {
   if (name == "igemm_pair") g_igemm_pair = value;
@@ -85,6 +87,7 @@ void set_variant(const std::string& name, int value) {
   else if (name == "prefix_share") g_prefix = value;
   else if (name == "igemm_ng4") g_ng4 = value;
   else if (name == "attn3") g_attn3 = value;
+  else if (name == "gn_epilogue") g_gn_epi = value;
   else DM_CHECK(false, "unknown kernel variant '" + name + "'");
 }
 
@@ -138,6 +141,28 @@ static int pick_bn(int N) {
   return best;
 }
 
+// M-tile shape: 2^wt x 2^ht x 2^nt = 128 pixels, minimal padding, widest rows preferred
+static void pick_mtile(int Nimg, int H, int W, int& wt_log, int& ht_log, int& nt_log) {
+  long long best = -1;
+  for (int wl = 7; wl >= 0; --wl)
+    for (int hl = 7 - wl; hl >= 0; --hl) {
+      const int nl = 7 - wl - hl;
+      const long long wt = 1 << wl, ht = 1 << hl, nt = 1 << nl;
+      const long long pad = ((W + wt - 1) / wt * wt) * ((H + ht - 1) / ht * ht) * ((Nimg + nt - 1) / nt * nt);
+      if (best < 0 || pad < best) { best = pad; wt_log = wl; ht_log = hl; nt_log = nl; }
+    }
+}
+
+
+bool igemm_gn_fusable(int H, int W, int N) {
+  if (N % 64 != 0 || (static_cast<long long>(H) * W) % IG_BM != 0) return false;
+  int wl = 0, hl = 0, nl = 0;
+  pick_mtile(2, H, W, wl, hl, nl);  // conv layout: the m-tile must be 2^hl x 2^wl pixels of ONE image, tiling it exactly
+  const int bn = pick_bn(N);
+  return nl == 0 && (W % (1 << wl)) == 0 && (H % (1 << hl)) == 0 && N % bn == 0 && bn >= 32;
+}
+size_t gn_record_floats(int Nimg, int HW, int C) { return static_cast<size_t>(Nimg) * (2 * (HW / IG_BM * 4) + 1) * C; }
+
 IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms) {
   IgemmOp op{};
   IgParams& p = op.p;
@@ -156,15 +181,7 @@ IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms) {
   p.nseg = d.nseg;
   p.k_iters = kit;
   p.Nimg = d.Nimg; p.H = d.H; p.W = d.W;
-  // M-tile shape: 2^wt x 2^ht x 2^nt = 128 pixels, minimal padding, widest rows preferred
-  long long best = -1;
-  for (int wl = 7; wl >= 0; --wl)
-    for (int hl = 7 - wl; hl >= 0; --hl) {
-      const int nl = 7 - wl - hl;
-      const long long wt = 1 << wl, ht = 1 << hl, nt = 1 << nl;
-      const long long pad = ((d.W + wt - 1) / wt * wt) * ((d.H + ht - 1) / ht * ht) * ((d.Nimg + nt - 1) / nt * nt);
-      if (best < 0 || pad < best) { best = pad; p.wt_log = wl; p.ht_log = hl; p.nt_log = nl; }
-    }
+  pick_mtile(d.Nimg, d.H, d.W, p.wt_log, p.ht_log, p.nt_log);
   const int wt = 1 << p.wt_log, ht = 1 << p.ht_log, nt = 1 << p.nt_log;
   p.tiles_x = (d.W + wt - 1) / wt;
   p.tiles_y = (d.H + ht - 1) / ht;
@@ -190,6 +207,16 @@ IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms) {
              static_cast<long long>((p.m_tiles + 1) / 2) * p.n_tiles >= num_sms / 2)))
               ? 2 : 1;
   DM_CHECK(d.loss == nullptr || (op.direct && !d.out_f32 && d.N >= 4), "igemm: the fused loss epilogue needs the direct fp16 epilogue");
+  if (d.gn.rec != nullptr) {
+    IgGn& g = p.gn;
+    g.rec = d.gn.rec;
+    g.tiles_img = d.gn.tiles_img ? d.gn.tiles_img : p.tiles_x * p.tiles_y;
+    // whole 128-pixel tiles, each inside one image; whole N-tiles; the staged fp16 epilogue
+    DM_CHECK(!op.direct && !d.geglu && d.bn == 0 && d.N % op.bn == 0 && d.N % 64 == 0 && p.nt_log == 0 &&
+                 d.W % (1 << p.wt_log) == 0 && d.H % (1 << p.ht_log) == 0 && p.m_tiles % g.tiles_img == 0 &&
+                 (d.gn.tiles_img == 0 || (d.Nimg == 1 && d.H == 1)),
+             "igemm: GroupNorm statistics in the epilogue need whole 128-pixel tiles per image and whole N-tiles");
+  }
   DM_CHECK(!d.geglu || (op.bn % 64 == 0 && !op.direct), "igemm: GEGLU needs an N-tile that is a multiple of 64");
   DM_CHECK(!d.geglu || (!d.residual && !d.rowbias && !d.act_silu), "igemm: GEGLU excludes the other epilogue options");
   if (!op.direct) {
@@ -518,6 +545,54 @@ void gn_launch(const GnDesc& d, cudaStream_t s) {
   DM_CUDA(cudaGetLastError());
 }
 
+bool gn_fold_apply_supported(int HW, int C0, int C1) {
+  const int C = C0 + C1;
+  return HW % 128 == 0 && C % 32 == 0 && C0 % 8 == 0 && C1 % 8 == 0 && C <= GN_FOLD_MAXC && C / 8 <= 256;
+}
+
+void gn_fold_apply_launch(const GnDesc& d, const float* rec0, const float* rec1, cudaStream_t s) {
+  const int C = d.C0 + d.C1;
+  DM_CHECK(gn_fold_apply_supported(d.HW, d.C0, d.C1) && d.Nimg <= 65535 && rec0 && (d.C1 == 0 || (rec1 && d.src1)) &&
+               d.ps0 == d.C0 && (d.C1 == 0 || d.ps1 == d.C1), "groupnorm fold+apply: bad arguments");
+  // (threads, CTAs per SM the registers are capped for, loads in flight, cluster size): the geometry is a function of the
+  // variant and of C alone, never of the batch
+  static const int var = env_or("DM_GNFA_VAR", 2);
+  static const int cl_env = env_or("DM_GNFA_CL", 8);
+  const int cl_base = (cl_env == 4 || cl_env == 16) ? cl_env : 8;
+  const int E = d.HW / 128 * 4;
+  const int VT = C / 8;
+  GnStatSrc s0{d.src0, rec0, d.C0}, s1{d.src1, rec1, d.C1};
+  auto go = [&](auto kernel, int threads) {
+    int CL = cl_base;
+    // a CTA folds C / CL channels with one thread per (slice, channel) and reduces its 32 / CL groups with one warp each
+    while (C / CL > threads || 32 / CL > threads / 32) CL *= 2;
+    DM_CHECK(CL <= 16 && VT <= threads, "groupnorm fold+apply: too many channels for this variant");
+    static bool configured[64] = {};
+    if (first_use_on_this_device(configured)) DM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(CL, d.Nimg, 1);
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int R = std::max(1, threads / VT);
+    DM_CUDA(cudaLaunchKernelEx(&cfg, kernel, s0, s1, d.HW, C / 32, (d.HW + CL - 1) / CL, VT, R, E, d.gamma, d.beta, d.eps, d.silu,
+                               d.out));
+  };
+  switch (var) {
+    case 1: go(gn_fold_apply_kernel<256, 3, 8>, 256); break;
+    case 4: go(gn_fold_apply_kernel<256, 5, 4>, 256); break;
+    case 0: go(gn_fold_apply_kernel<384, 2, 8>, 384); break;
+    default: go(gn_fold_apply_kernel<256, 4, 6>, 256); break;
+  }
+}
+
 void layernorm_launch(const __half* x, long long ld_x, const float* gamma, const float* beta, float eps, long long rows,
                       int C, __half* out, long long ld_out, cudaStream_t s) {
   DM_CHECK(C % 8 == 0 && C <= 1280, "layernorm: C must be a multiple of 8 and <= 1280");
@@ -535,6 +610,31 @@ void layernorm_launch(const __half* x, long long ld_x, const float* gamma, const
     kernel<<<blocks, 256, smem, s>>>(x, ld_x, gamma, beta, eps, rows, C, out, ld_out);
   };
   static int occ2 = 0, occ3 = 0, occ5 = 0;
+  // the three Transformer2DModel widths: every lane busy (LPR lanes x 5 vectors per row)
+  static const int ln_var = env_or("DM_LN_VAR", 2);
+  if (ln_var && (C == 320 || C == 640 || C == 1280)) {
+    auto launch5 = [&](auto kernel, int rpw, int& occ_cache, size_t dyn_smem) {
+      if (occ_cache == 0) {
+        DM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, kernel, 256, dyn_smem));
+        occ_cache = std::max(1, occ_cache);
+      }
+      const long long want5 = (rows + 8 * rpw - 1) / (8 * rpw);
+      const unsigned blocks = static_cast<unsigned>(std::max<long long>(1, std::min<long long>(want5, 148ll * occ_cache)));
+      kernel<<<blocks, 256, dyn_smem, s>>>(x, ld_x, gamma, beta, eps, rows, out, ld_out);
+    };
+    static int o8 = 0, o16 = 0, o32 = 0, p8 = 0, p16 = 0, p32 = 0;
+    if (ln_var == 2) {  // default: occupancy instead of a register prefetch, fp16 gamma / beta in (static) shared memory
+      if (C == 320) launch5(layernorm5b_kernel<8, 4>, 4, p8, 0);
+      else if (C == 640) launch5(layernorm5b_kernel<16, 4>, 2, p16, 0);
+      else launch5(layernorm5b_kernel<32, 4>, 1, p32, 0);
+    } else {
+      if (C == 320) launch5(layernorm5_kernel<8>, 4, o8, smem);
+      else if (C == 640) launch5(layernorm5_kernel<16>, 2, o16, smem);
+      else launch5(layernorm5_kernel<32>, 1, o32, smem);
+    }
+    DM_CUDA(cudaGetLastError());
+    return;
+  }
   if (maxv <= 2) launch(layernorm_kernel<2>, occ2);
   else if (maxv == 3) launch(layernorm_kernel<3>, occ3);
   else launch(layernorm_kernel<5>, occ5);

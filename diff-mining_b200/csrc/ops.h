@@ -54,6 +54,13 @@ struct IgemmDesc {
   long long ld_out = 0;
   int out_f32 = 0, geglu = 0, act_silu = 0;
   const IgLossArgs* loss = nullptr;  // device-resident typicality epilogue arguments (conv_out, direct epilogue only)
+  // GroupNorm statistics of the output formed in the epilogue (igemm.cuh: IgGn): rec = per-image records
+  // [(2 * 4 * tiles_img + 1) * N floats]; tiles_img = 128-pixel tiles per image (0 = tiles_x * tiles_y, the conv layout;
+  // a flattened Linear passes H * W / 128)
+  struct {
+    float* rec = nullptr;  // null: off
+    int tiles_img = 0;
+  } gn;
   int bn = 0;  // 0 = choose
   int cg = 0;  // CTAs per tile: 0 = choose, 1 = single CTA, 2 = CTA pair (cta_group::2)
 };
@@ -70,6 +77,11 @@ struct IgemmOp {
 
 void set_variant(const std::string& name, int value);  // "igemm_pair" / "gn_fused": 0, 1, or -1 = default
 IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms);
+// true when a conv / Linear writing fp16 [Nimg, H*W, N] through the staged epilogue can form GroupNorm statistics there:
+// whole 128-pixel tiles per image and whole N-tiles (holds for the conv layout and for the flattened Linear layout)
+bool igemm_gn_fusable(int H, int W, int N);
+size_t gn_record_floats(int Nimg, int HW, int C);  // size of the statistics record of an [Nimg, HW, C] tensor
+int gn_epilogue_mode();  // variant "gn_epilogue" (DM_GN_EPILOGUE) bit mask: 1 = 3x3 convs, 2 = 1x1 convs / Linears form statistics
 void igemm_launch(const IgemmOp& op, cudaStream_t s);
 // convenience segment builders
 void seg_conv3x3(IgemmDesc& d, int Cin_total, int C0);           // 9 taps over src0 (C0 ch) [+ src1]
@@ -116,6 +128,11 @@ struct GnDesc {
 int gn_splits(int Nimg, int HW);
 int gn_launch_count(int HW, int C);  // kernels gn_launch() issues for this shape (1 = cluster-fused, 2 = stats + apply)
 void gn_launch(const GnDesc& d, cudaStream_t s);
+// GroupNorm over one or two dense sources whose statistics records the producing convs' epilogues left in rec0 / rec1
+// (igemm.cuh: IgGn): fold + apply in one cluster kernel.  d.src0/C0 [, d.src1/C1], d.Nimg, d.HW, gamma / beta / eps / silu /
+// out are read.  Requires HW % 128 == 0, C0 + C1 <= 2048, C0 and C1 multiples of 8, (C0 + C1) % 32 == 0.
+bool gn_fold_apply_supported(int HW, int C0, int C1);
+void gn_fold_apply_launch(const GnDesc& d, const float* rec0, const float* rec1, cudaStream_t s);
 void layernorm_launch(const __half* x, long long ld_x, const float* gamma, const float* beta, float eps, long long rows,
                       int C, __half* out, long long ld_out, cudaStream_t s);
 void patch3x3_launch(const float* x0, const int* x_index, const float* noise, const int* noise_index, const long long* t,

@@ -24,8 +24,23 @@ struct Builder {
   size_t alloc_bytes(size_t bytes) { return ar.alloc((bytes + 1023) & ~size_t(1023)); }
   void release(Act& a) {
     if (!a.valid) return;
-    if (!e.debug_keep) ar.free(a.off);
+    if (!e.debug_keep) {
+      ar.free(a.off);
+      if (a.stats) ar.free(a.st_off);
+    }
     a.valid = false;
+    a.stats = false;
+  }
+  // ---- GroupNorm statistics in the producer's epilogue.  kind: 1 = 3x3 conv, 2 = 1x1 conv / Linear (variant gn_epilogue)
+  bool gn_fusable(int kind, int H, int W, int C) const {
+    return (gn_epilogue_mode() & kind) != 0 && igemm_gn_fusable(H, W, C);
+  }
+  // reserve the statistics record of output `o` and point the conv at it
+  void attach_stats(Act& o, IgemmDesc& d, bool flattened) {
+    o.st_off = alloc_bytes(gn_record_floats(o.N, o.H * o.W, o.C) * sizeof(float));
+    o.stats = true;
+    d.gn.rec = at<float>(o.st_off);
+    d.gn.tiles_img = flattened ? o.H * o.W / 128 : 0;
   }
   void tap(const std::string& name, const Act& a) {
     if (e.debug_keep && !dry) p.taps[name] = a;
@@ -50,10 +65,13 @@ struct Builder {
     push(Step{[op](cudaStream_t s) { attn_launch(op, s); }, kStepAttn, op.flops, 1, name});
   }
 
-  // ---- GroupNorm(+SiLU) over one or two sources -> dense normalised tensor
+  // ---- GroupNorm(+SiLU) over one or two sources -> dense normalised tensor.  When every source carries the statistics
+  // record its producer's epilogue formed, one cluster kernel folds the records and applies y = x * a + b (1 read + 1
+  // write); otherwise the stand-alone kernels read the sources twice.
   Act groupnorm(const std::string& name, const Act& x0, const Act* x1, const std::string& wkey, float eps, bool silu) {
     const int C = x0.C + (x1 ? x1->C : 0);
     Act o = alloc(x0.N, x0.H, x0.W, C);
+    const bool from_stats = x0.stats && (!x1 || x1->stats) && gn_fold_apply_supported(x0.H * x0.W, x0.C, x1 ? x1->C : 0);
     if (!dry) {
       GnDesc d;
       d.src0 = hp(x0); d.C0 = x0.C; d.ps0 = x0.C;
@@ -61,19 +79,26 @@ struct Builder {
       d.Nimg = x0.N; d.HW = x0.H * x0.W;
       d.gamma = e.F(wkey + ".weight"); d.beta = e.F(wkey + ".bias");
       d.eps = eps; d.silu = silu ? 1 : 0;
-      d.partial = e.gn_partial; d.ab = e.gn_ab; d.tickets = e.gn_tickets;
-      DM_CHECK(static_cast<size_t>(2) * C * x0.N * gn_splits(x0.N, d.HW) <= e.gn_partial_floats &&
-                   static_cast<size_t>(2) * x0.N * C <= e.gn_ab_floats && static_cast<size_t>(x0.N) <= e.gn_ticket_count,
-               "GroupNorm scratch too small");
       d.out = hp(o);
-      push(Step{[d](cudaStream_t s) { gn_launch(d, s); }, kStepOther, 0, gn_launch_count(d.HW, C), name});
+      if (from_stats) {
+        const float* r0 = at<float>(x0.st_off);
+        const float* r1 = x1 ? at<float>(x1->st_off) : nullptr;
+        push(Step{[d, r0, r1](cudaStream_t s) { gn_fold_apply_launch(d, r0, r1, s); }, kStepOther, 0, 1, name + ".apply"});
+      } else {
+        d.partial = e.gn_partial; d.ab = e.gn_ab; d.tickets = e.gn_tickets;
+        DM_CHECK(static_cast<size_t>(2) * C * x0.N * gn_splits(x0.N, d.HW) <= e.gn_partial_floats &&
+                     static_cast<size_t>(2) * x0.N * C <= e.gn_ab_floats && static_cast<size_t>(x0.N) <= e.gn_ticket_count,
+                 "GroupNorm scratch too small");
+        push(Step{[d](cudaStream_t s) { gn_launch(d, s); }, kStepOther, 0, gn_launch_count(d.HW, C), name});
+      }
     }
     return o;
   }
 
-  // ---- 3x3 stride-1 conv over (x0 [+ x1]); epilogue options
+  // ---- 3x3 stride-1 conv over (x0 [+ x1]); epilogue options.  gn_stats: the output will be read by a GroupNorm, so the
+  // epilogue also forms its statistics record where the shape allows (Act::stats)
   Act conv3x3(const std::string& name, const Act& x0, const Act* x1, const std::string& wkey, int Cout,
-              const __half* rowbias, int ld_rowbias, const Act* residual) {
+              const __half* rowbias, int ld_rowbias, const Act* residual, bool gn_stats = false) {
     Act o = alloc(x0.N, x0.H, x0.W, Cout);
     IgemmDesc d;
     d.Nimg = x0.N; d.H = x0.H; d.W = x0.W;
@@ -88,13 +113,14 @@ struct Builder {
     d.rowbias = rowbias; d.ld_rowbias = ld_rowbias;
     if (residual) { d.residual = hp(*residual); d.ld_res = residual->C; }
     d.out = hp(o); d.ld_out = Cout;
+    if (gn_stats && gn_fusable(1, o.H, o.W, Cout)) attach_stats(o, d, false);
     add_igemm(name, d);
     return o;
   }
 
   // ---- 1x1 conv / Linear over (x0 [+ x1]) viewed as [M, C]
   Act linear(const std::string& name, const Act& x0, const Act* x1, const std::string& wkey, int Nout, bool has_bias,
-             const Act* residual, bool geglu = false, bool silu = false) {
+             const Act* residual, bool geglu = false, bool silu = false, bool gn_stats = false) {
     const int Cout = geglu ? Nout / 2 : Nout;
     Act o = alloc(x0.N, x0.H, x0.W, Cout);
     IgemmDesc d;
@@ -111,6 +137,8 @@ struct Builder {
     if (residual) { d.residual = hp(*residual); d.ld_res = residual->C; }
     d.out = hp(o); d.ld_out = Cout;
     d.geglu = geglu ? 1 : 0; d.act_silu = silu ? 1 : 0;
+    // gn_stats: the output will be read by a GroupNorm -- form its statistics record in the epilogue where the shape allows
+    if (gn_stats && !geglu && gn_fusable(2, o.H, o.W, Cout)) attach_stats(o, d, true);
     add_igemm(name, d);
     return o;
   }

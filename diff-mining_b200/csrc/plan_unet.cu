@@ -14,12 +14,14 @@ struct UnetBuilder : Builder {
   int tproj_row_mult = 1;   // > 1 while building the shared prefix: row u of the activations <-> row u*G of tproj
   using Builder::Builder;
 
-  // ResnetBlock2D (reference op order: applications/parallel-dataset/pnp.py:282-359)
+  // ResnetBlock2D (reference op order: applications/parallel-dataset/pnp.py:282-359).  Every conv whose output is read by
+  // a GroupNorm (conv1 -> norm2; conv2 -> the next block's norm / norm1, directly or as a skip connection) also forms that
+  // GroupNorm's statistics in its epilogue, so the normalisation is a single fold + apply pass.
   Act resnet(const std::string& key, const Act& x0, const Act* x1, int Cout) {
     const int Cin = x0.C + (x1 ? x1->C : 0);
     Act n1 = groupnorm(key + ".norm1", x0, x1, key + ".norm1", 1e-5f, true);
     const __half* rb = dry ? nullptr : tproj + e.tproj_off.at(key);
-    Act h1 = conv3x3(key + ".conv1", n1, nullptr, key + ".conv1", Cout, rb, e.tproj_total * tproj_row_mult, nullptr);
+    Act h1 = conv3x3(key + ".conv1", n1, nullptr, key + ".conv1", Cout, rb, e.tproj_total * tproj_row_mult, nullptr, true);
     release(n1);
     Act n2 = groupnorm(key + ".norm2", h1, nullptr, key + ".norm2", 1e-5f, true);
     release(h1);
@@ -29,7 +31,7 @@ struct UnetBuilder : Builder {
       sc = linear(key + ".conv_shortcut", x0, x1, key + ".conv_shortcut", Cout, true, nullptr);
       res = &sc;
     }
-    Act out = conv3x3(key + ".conv2", n2, nullptr, key + ".conv2", Cout, nullptr, 0, res);
+    Act out = conv3x3(key + ".conv2", n2, nullptr, key + ".conv2", Cout, nullptr, 0, res, true);
     release(n2);
     release(sc);
     tap(key, out);
@@ -98,7 +100,7 @@ struct UnetBuilder : Builder {
     Act h4 = linear(t + ".ff.net.2", g, nullptr, t + ".ff.net.2", C, true, &h3);
     release(g);
     release(h3);
-    Act out = linear(key + ".proj_out", h4, nullptr, key + ".proj_out", C, true, &x);
+    Act out = linear(key + ".proj_out", h4, nullptr, key + ".proj_out", C, true, &x, false, false, true);
     release(h4);
     tap(key, out);
     return out;
@@ -109,14 +111,25 @@ struct UnetBuilder : Builder {
     return transformer_tail(key, x, h2);
   }
 
-  // replicate every row of x (N = groups) G times -> N*G rows (cond/uncond prefix sharing)
-  Act repeat_rows(const std::string& name, const Act& x, int G) {
+  // replicate every row of x (N = groups) G times -> N*G rows (cond/uncond prefix sharing); with_stats: the copy will be
+  // read by a GroupNorm (skip connection), so x's statistics record is replicated with it
+  Act repeat_rows(const std::string& name, const Act& x, int G, bool with_stats = false) {
     Act o = alloc(x.N * G, x.H, x.W, x.C);
+    if (with_stats && x.stats) {
+      o.st_off = alloc_bytes(gn_record_floats(o.N, o.H * o.W, o.C) * sizeof(float));
+      o.stats = true;
+    }
     if (!dry) {
       const __half* in = hp(x);
       __half* out = hp(o);
       const long long rows = x.N, elems = static_cast<long long>(x.H) * x.W * x.C;
       push(Step{[=](cudaStream_t s) { repeat_rows_launch(in, rows, elems, G, out, s); }, kStepOther, 0, 1, name});
+      if (o.stats) {
+        const __half* sin = at<__half>(x.st_off);
+        __half* sout = at<__half>(o.st_off);
+        const long long selems = static_cast<long long>(gn_record_floats(1, x.H * x.W, x.C)) * 2;  // floats as half pairs
+        push(Step{[=](cudaStream_t s) { repeat_rows_launch(sin, rows, selems, G, sout, s); }, kStepOther, 0, 1, name + ".stats"});
+      }
     }
     return o;
   }
@@ -141,6 +154,7 @@ struct UnetBuilder : Builder {
     d.N = x.C; d.K = 9 * x.C;
     d.bias = dry ? nullptr : e.F(key + ".conv.bias");
     d.out = hp(o); d.ld_out = x.C;
+    if (gn_fusable(1, H2, W2, x.C)) attach_stats(o, d, false);  // read by the next block's norm1 and, as a skip, by the up path
     add_igemm(key + ".conv", d);
     release(planes);
     tap(key, o);
@@ -156,7 +170,7 @@ struct UnetBuilder : Builder {
       push(Step{[=](cudaStream_t s) { upsample_nearest_launch(in, N, H, W, C, Ho, Wo, out, s); }, kStepOther, 0, 1,
                 key + ".nearest"});
     }
-    Act o = conv3x3(key + ".conv", up, nullptr, key + ".conv", x.C, nullptr, 0, nullptr);
+    Act o = conv3x3(key + ".conv", up, nullptr, key + ".conv", x.C, nullptr, 0, nullptr, true);
     release(up);
     tap(key, o);
     return o;
@@ -203,7 +217,7 @@ void build_unet_plan(Engine& e, Plan& p, bool dry, ArenaPlanner& ar) {
 
   // ---- conv_in as a K=64 GEMM over the 36-wide 3x3x4 patch matrix
   Act ain; ain.off = off_ain; ain.N = Bu; ain.H = h; ain.W = w; ain.C = 64; ain.valid = true;
-  Act x = b.linear("conv_in", ain, nullptr, U + "conv_in", 320, true, nullptr);
+  Act x = b.linear("conv_in", ain, nullptr, U + "conv_in", 320, true, nullptr, false, false, true);
   b.tap("conv_in", x);
 
   std::vector<Act> skips;
@@ -219,7 +233,7 @@ void build_unet_plan(Engine& e, Plan& p, bool dry, ArenaPlanner& ar) {
         Act r_u = b.resnet(rk, x, nullptr, ch[i]);
         b.tproj_row_mult = 1;
         Act h2_u = b.transformer_head(ak, r_u);
-        Act s0 = b.repeat_rows("conv_in.fanout", x, G);
+        Act s0 = b.repeat_rows("conv_in.fanout", x, G, true);
         b.release(x);
         skips.push_back(s0);
         Act r_f = b.repeat_rows(rk + ".fanout", r_u, G);
@@ -264,11 +278,11 @@ void build_unet_plan(Engine& e, Plan& p, bool dry, ArenaPlanner& ar) {
       Act skip = skips.back();
       skips.pop_back();
       const std::string rk = U + "up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j);
+      const std::string ak = U + "up_blocks." + std::to_string(i) + ".attentions." + std::to_string(j);
       Act r = b.resnet(rk, x, &skip, up_out[i]);
       b.release(x);
       b.release(skip);
       if (i > 0) {
-        const std::string ak = U + "up_blocks." + std::to_string(i) + ".attentions." + std::to_string(j);
         Act a = b.transformer(ak, r);
         b.release(r);
         r = a;

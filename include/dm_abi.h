@@ -134,11 +134,20 @@ int64_t dm_patch_topk_work_floats(int B, int H, int W, int ky);
 int dm_op_conv(const void* x, const void* x2, int N, int H, int W, int C0, int C1, const void* w, int Cout, int ks,
                int stride, int vae_pad, const float* bias, const void* rowbias, const void* residual, void* out,
                int out_f32, int geglu, int act_silu, int bn, void* stream);
+/* 3x3 / 1x1 stride-1 conv over ONE source whose epilogue also forms the GroupNorm(32 groups) statistics of its output
+ * (igemm.cuh: IgGn), followed by the fold + apply kernel (norm.cuh: gn_fold_apply_kernel) -- the pair the engine uses for
+ * conv1 -> norm2 and conv2 -> Transformer2DModel.norm.  out = conv output fp16 [N*H*W, Cout]; gn_out =
+ * GroupNorm(+SiLU)(out) fp16.  Errors when H*W is not made of whole 128-pixel tiles or Cout not of whole N-tiles. */
+int dm_op_conv_gn(const void* x, int N, int H, int W, int C0, const void* w, int Cout, int ks, const float* bias,
+                  const void* rowbias, const void* residual, const float* gamma, const float* beta, float eps, int silu,
+                  void* out, void* gn_out, void* stream);
 int dm_op_attention(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t bs_q,
                     int64_t bs_k, int64_t bs_v, int B, int heads, int D, int Tq, int Tk, int kv_batches,
                     const int32_t* kv_index_dev, void* out, int64_t ld_out, void* stream);
 int dm_op_groupnorm(const void* x, const void* x2, int N, int HW, int C0, int C1, const float* gamma, const float* beta,
                     float eps, int silu, void* out, void* stream);
+/* LayerNorm over the last dim.  At C = 320 / 640 / 1280 gamma and beta are rounded to fp16 inside the kernel (they are fp16
+ * weights in the engine, where the fp32 copies convert back exactly). */
 int dm_op_layernorm(const void* x, int64_t rows, int C, const float* gamma, const float* beta, float eps, void* out,
                     void* stream);
 /* kernel-variant switches for tests / A-B timing (affect ops prepared afterwards; -1 = built-in default):
@@ -149,6 +158,9 @@ int dm_op_layernorm(const void* x, int64_t rows, int C, const float* gamma, cons
  *   xattn       1 = short-key-set cross-attention kernel (P in tensor memory), 0 = generic flash kernel
  *   attn3       persistent self-attention kernel (attention3.cuh): 1 = two softmax threads per query row, 2 = one thread per
  *               row; 0 = one CTA per 256-query block (attention2.cuh)
+ *   gn_epilogue bit mask: 1 = 3x3 convs, 2 = 1x1 convs / Linears form the GroupNorm statistics of their output in the
+ *               epilogue (igemm.cuh: IgGn) and the GroupNorm becomes one fold + apply pass; 0 = stand-alone GroupNorm
+ *               kernels everywhere.  Default 3.  Takes effect for plans built afterwards.
  *   prefix_share 1 = dm_typicality computes the context-free U-Net prefix once per (eps,t) draw (bit-identical) */
 int dm_op_set_variant(const char* name, int value);
 

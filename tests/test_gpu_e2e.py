@@ -99,6 +99,39 @@ def test_layerwise_parity(engine, unet_weights_gpu, contexts):
         engine.debug_keep(False)
 
 
+def test_groupnorm_statistics_from_conv_epilogue(engine, unet_weights_gpu, contexts):
+    """every conv / Linear whose output feeds a GroupNorm (conv1 -> norm2, conv2 / proj_out / conv_in / down- and
+    up-samplers -> the next norm, also through the skip connections and the cat of the up path) forms that GroupNorm's
+    statistics in its epilogue (igemm.cuh: IgGn) wherever an image is made of whole 128-pixel tiles; the result must agree
+    with the stand-alone GroupNorm kernels to fp16 rounding noise, stay inside the parity gate, and be deterministic and
+    batch-invariant.  Modes: 3 = all producers, 1 = 3x3 convs only, 0 = off."""
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(3, 4, 32, 32, generator=g)
+    t = torch.tensor([10, 500, 990])
+    slots = [0, 1, 2]
+    ctx = torch.stack([contexts[s] for s in slots]).to(DEV)
+    with torch.no_grad():
+        gold = sd15.unet_forward(unet_weights_gpu, x.to(DEV), t.to(DEV), ctx)
+        ac = sd15.unet_forward(half_weights(unet_weights_gpu), x.to(DEV), t.to(DEV), ctx, autocast=True)
+    outs = {}
+    try:
+        for mode in (3, 1, 0):
+            engine.set_variant("gn_epilogue", mode)
+            engine.debug_keep(True)   # toggling drops the cached plans: the next forward is planned with the current variant
+            engine.debug_keep(False)
+            outs[mode] = engine.unet_eps(x, t, slots)
+            assert torch.equal(outs[mode], engine.unet_eps(x, t, slots))
+            noise_floor_gate(outs[mode], gold, ac, f"unet eps, gn_epilogue={mode}")
+            # image independence: row 1 alone == row 1 inside the batch
+            assert torch.equal(engine.unet_eps(x[1:2], t[1:2], slots[1:2])[0], outs[mode][1])
+    finally:
+        engine.set_variant("gn_epilogue", -1)
+        engine.debug_keep(True)
+        engine.debug_keep(False)
+    # two fp16 pipelines: rounding noise (2.1e-3 measured), both inside the gate
+    assert max_rel(outs[3], outs[0]) < 5e-3 and max_rel(outs[1], outs[0]) < 5e-3
+
+
 def reference_grid(unet_w, contexts, x0, noise, t, slots):
     """D.compute_losses (compute.py:134-160) restated with the oracle: [Bi, N, n_cond, 4, h, w] fp32"""
     Bi, N = x0.shape[0], noise.shape[0]

@@ -148,6 +148,63 @@ def test_groupnorm_two_kernel_path_matches_fused(lib):
     assert max_rel(outs[0], outs[1]) < 1e-3
 
 
+CONV_GN_CASES = [
+    # N, H, W, Cin, Cout, ks, rowbias, residual, silu, bias mean, igemm_pair, igemm_ng4
+    (3, 32, 32, 320, 320, 3, 1, 0, 1, 0.0, -1, -1),     # conv1 -> norm2 (+ time embedding)
+    (2, 64, 64, 320, 320, 3, 0, 1, 0, 0.0, -1, -1),     # conv2 (+ residual) -> Transformer2DModel.norm, 32 tiles / image
+    (5, 16, 16, 640, 1280, 3, 1, 0, 1, 0.0, -1, -1),    # two tiles per image, 1280 channels
+    (2, 32, 32, 640, 640, 3, 1, 1, 1, 50.0, -1, -1),    # channel means >> std (cancellation-free sums)
+    (3, 16, 32, 320, 640, 3, 1, 0, 1, 0.0, 2, -1),      # CTA pairs
+    (2, 32, 32, 320, 320, 3, 0, 1, 1, 0.0, 0, 2),       # four epilogue warpgroups
+    (2, 32, 32, 320, 320, 1, 0, 1, 0, 0.0, -1, -1),     # 1x1
+]
+
+
+@pytest.mark.parametrize("case", CONV_GN_CASES, ids=lambda c: "-".join(map(str, c)))
+def test_conv_with_groupnorm_statistics_in_the_epilogue(lib, case):
+    """conv whose epilogue forms the GroupNorm statistics of its output + the fold/apply kernel (igemm.cuh: IgGn,
+    norm.cuh: gn_fold_apply_kernel) against conv2d -> fp16 -> group_norm in fp32; the conv output itself must be
+    bit-identical to the plain conv, and both outputs deterministic and independent of the batch an image is in"""
+    N, H, W, Cin, Cout, ks, rowbias, residual, silu, bmean, pair, ng4 = case
+    g = torch.Generator(device="cuda").manual_seed(99 + N + H + Cin + Cout)
+    x = torch.randn(N, H, W, Cin, device="cuda", generator=g).half()
+    w = (torch.randn(Cout, Cin, ks, ks, device="cuda", generator=g) / math.sqrt(Cin * ks * ks)).half()
+    b = (torch.randn(Cout, device="cuda", generator=g) + bmean * torch.randn(Cout, device="cuda", generator=g).sign()).half().float()
+    rb = torch.randn(N, Cout, device="cuda", generator=g).half() if rowbias else None
+    rs = (torch.randn(N * H * W, Cout, device="cuda", generator=g) + 2.0).half() if residual else None
+    gamma = torch.randn(Cout, device="cuda", generator=g)
+    beta = torch.randn(Cout, device="cuda", generator=g)
+    check(lib, lib.dm_op_set_variant(b"igemm_pair", pair))
+    check(lib, lib.dm_op_set_variant(b"igemm_ng4", ng4))
+    try:
+        def run(n0, n1):
+            n = n1 - n0
+            out = torch.full((n * H * W, Cout), float("nan"), device="cuda", dtype=torch.float16)
+            gn = torch.full_like(out, float("nan"))
+            check(lib, lib.dm_op_conv_gn(ptr(x[n0:n1].contiguous()), n, H, W, Cin, ptr(pack_w(w)), Cout, ks, ptr(b),
+                                         ptr(rb[n0:n1].contiguous()) if rowbias else None,
+                                         ptr(rs[n0 * H * W:n1 * H * W].contiguous()) if residual else None,
+                                         ptr(gamma), ptr(beta), 1e-5, silu, ptr(out), ptr(gn), stream()))
+            torch.cuda.synchronize()
+            return out, gn
+        out, gn = run(0, N)
+        out_b, gn_b = run(0, N)
+        assert torch.equal(out, out_b) and torch.equal(gn, gn_b)
+        plain = torch.full_like(out, float("nan"))
+        check(lib, lib.dm_op_conv(ptr(x), None, N, H, W, Cin, 0, ptr(pack_w(w)), Cout, ks, 1, 0, ptr(b), ptr(rb), ptr(rs),
+                                  ptr(plain), 0, 0, 0, 0, stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(out, plain)
+        ref = F.group_norm(out.float().view(N, H * W, Cout).permute(0, 2, 1), 32, gamma, beta, 1e-5)
+        ref = (F.silu(ref) if silu else ref).permute(0, 2, 1).reshape(N * H * W, Cout)
+        assert max_rel(gn, ref) < 2e-3
+        out1, gn1 = run(N - 1, N)  # the last image alone
+        assert torch.equal(gn1, gn[(N - 1) * H * W:])
+    finally:
+        check(lib, lib.dm_op_set_variant(b"igemm_ng4", -1))
+        check(lib, lib.dm_op_set_variant(b"igemm_pair", -1))
+
+
 ATTN_CASES = [
     # B, Tq, Tk, D, cross
     (1, 128, 128, 40, 0), (2, 4096, 4096, 40, 0), (2, 1024, 1024, 80, 0), (2, 256, 256, 160, 0), (3, 64, 64, 160, 0),

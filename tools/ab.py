@@ -1,6 +1,9 @@
 """A/B timing + correctness of kernel variants through the op-level C ABI (development aid, run under gpurun).
    python tools/ab.py attn      self-attention shapes of the U-Net, every value of the `attn3` switch
    python tools/ab.py gn        GroupNorm shapes, fused vs two-kernel
+   python tools/ab.py norm      the streaming normalisation kernels at the U-Net's big shapes (LayerNorm, conv + epilogue
+                                statistics + fold/apply GroupNorm, stand-alone GroupNorm): event times, or the target of an
+                                ncu capture (variants are per-process: DM_LN_VAR, DM_GNFA_VAR, DM_GNFA_CL)
 Times: CUDA events on the launching stream, median of `reps` launches after warm-up; inputs are larger than L2 at the
 big shapes."""
 import ctypes
@@ -114,5 +117,30 @@ def stress():
         o.check(lib.dm_op_set_variant(b"attn3", -1))
 
 
+def norm():
+    lib.dm_op_conv_gn.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + \
+        [ctypes.c_void_p] * 5 + [ctypes.c_float, ctypes.c_int] + [ctypes.c_void_p] * 3
+    for rows, C in [(54 * 4096, 320), (54 * 1024, 640), (54 * 256, 1280)]:
+        x = torch.randn(rows, C, device="cuda").half()
+        gm, bt = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+        out = torch.empty_like(x)
+        f = lambda: o.check(lib.dm_op_layernorm(ptr(x), rows, C, ptr(gm), ptr(bt), 1e-5, ptr(out), stream()))  # noqa: E731
+        med, mn = timeit(f)
+        print(f"LN rows={rows} C={C}: {med:8.4f} ms (min {mn:.4f})  {2.0 * x.numel() * 2 / med / 1e6:7.1f} GB/s algorithmic", flush=True)
+    for (N, H, C, silu) in [(54, 64, 320, 1), (54, 64, 320, 0), (54, 32, 640, 1)]:
+        x = torch.randn(N, H, H, C, device="cuda").half()
+        w = (torch.randn(C, 9 * C, device="cuda") / (3 * C ** 0.5)).half()
+        b = torch.randn(C, device="cuda")
+        gm, bt = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+        out = torch.empty(N * H * H, C, device="cuda", dtype=torch.float16)
+        gno = torch.empty_like(out)
+        for _ in range(3):
+            o.check(lib.dm_op_conv_gn(ptr(x), N, H, H, C, ptr(w), C, 3, ptr(b), None, None, ptr(gm), ptr(bt), 1e-5, silu, ptr(out),
+                                      ptr(gno), stream()))
+        o.check(lib.dm_op_groupnorm(ptr(out), None, N, H * H, C, 0, ptr(gm), ptr(bt), 1e-5, silu, ptr(gno), stream()))
+        torch.cuda.synchronize()
+        print(f"CONV+GN N={N} H={H} C={C} silu={silu}: launched (time it with ncu / the layers profile)", flush=True)
+
+
 if __name__ == "__main__":
-    {"attn": attn, "gn": gn, "stress": stress}[sys.argv[1]]()
+    {"attn": attn, "gn": gn, "stress": stress, "norm": norm}[sys.argv[1]]()
