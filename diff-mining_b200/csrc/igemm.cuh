@@ -94,25 +94,36 @@ struct IgParams {
 // rows of A and HALF of the B tile, which cuts the per-SM shared-memory operand traffic and the L2 -> SM weight
 // traffic by the B half.
 // NG = epilogue warpgroups (2, or 4 for the short-K layers whose epilogue, not the MMA, bounds the tile time).
-template <int BN, bool DIRECT, int CG = 1, int NG = 2>
+// WS = weight-stationary (CTA pairs, K <= 64 * IG_WS_KCHUNKS): the unit's B tile (all k-chunks of ONE N-tile, half per CTA)
+// is loaded once and stays in shared memory while the unit walks down the M dimension; the pipeline stages carry A only.
+// The K = 320 Linears at 64x64 are bound by L2 -> SM traffic (the LTS throughput cap), 55 % of which is the weight tile
+// being re-fetched for every output tile.
+constexpr int IG_WS_KCHUNKS = 5;
+template <int BN, bool DIRECT, int CG = 1, int NG = 2, bool WS = false>
 struct IgCfg {
   static constexpr int THREADS = 64 + 128 * NG;
   static constexpr int A_BYTES = IG_BM * IG_BK * 2;
   static constexpr int B_BYTES = (BN / CG) * IG_BK * 2;
   static_assert(CG == 1 || (CG == 2 && !DIRECT && BN % 32 == 0), "CTA pairs: staged epilogue, BN multiple of 32");
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static_assert(!WS || (CG == 2 && !DIRECT), "weight-stationary: CTA pairs, staged epilogue");
+  static constexpr int W_BYTES = WS ? IG_WS_KCHUNKS * B_BYTES : 0;  // resident weight chunks
+  static constexpr int STAGE_BYTES = WS ? A_BYTES : A_BYTES + B_BYTES;
+#ifdef IG_RING_SMALL  // experiment: two chunk buffers per group everywhere (one more pipeline stage at BN = 160)
+  static constexpr int NBG = DIRECT ? 0 : 2;
+#else
   static constexpr int NBG = DIRECT ? 0 : (BN >= 256 || NG > 2) ? 2 : 4;  // chunk buffers per epilogue warpgroup
+#endif
   static constexpr int LOOKAHEAD = NBG >= 4 ? 2 : 1;             // residual prefetch distance (chunks)
   static constexpr int RING_BYTES = NG * NBG * IG_CHUNK_BYTES;
   static constexpr int BIAS_BYTES = NG * BN * 4;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int RAW_STAGES = (232448 - RING_BYTES - BIAS_BYTES - BAR_BYTES) / STAGE_BYTES;
+  static constexpr int RAW_STAGES = (232448 - RING_BYTES - BIAS_BYTES - BAR_BYTES - W_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RING_BYTES + BIAS_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + W_BYTES + RING_BYTES + BIAS_BYTES + BAR_BYTES;
   static_assert(STAGES >= 3, "pipeline too shallow");
-  static_assert(2 * STAGES + 4 + NG * (NBG > 0 ? NBG : 1) + 1 <= BAR_BYTES / 8, "barrier area");
-  static_assert(NG == 2 || (NG == 4 && !DIRECT && CG == 1), "four epilogue groups: staged epilogue, single CTA");
+  static_assert(2 * STAGES + 4 + NG * (NBG > 0 ? NBG : 1) + 2 <= BAR_BYTES / 8, "barrier area");
+  static_assert(NG == 2 || (NG == 4 && !DIRECT && (CG == 1 || WS)), "four epilogue groups: staged epilogue, single CTA or weight-stationary pair");
 };
 
 // Phi(x) * x with erfc from Abramowitz-Stegun 7.1.26 (|abs err| < 4.3e-7 on the result: within one fp16 ulp of
@@ -139,16 +150,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int BN, bool DIRECT, int CG, int NG>
+template <int BN, bool DIRECT, int CG, int NG, bool WS = false>
 __global__ void __launch_bounds__(64 + 128 * NG, 1) igemm_kernel(const __grid_constant__ IgMaps maps, const IgParams p) {
-  using Cfg = IgCfg<BN, DIRECT, CG, NG>;
+  using Cfg = IgCfg<BN, DIRECT, CG, NG, WS>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NBG = Cfg::NBG;
   extern __shared__ __align__(1024) uint8_t smem[];  // 128B-swizzled tiles need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* smA = smem;
   uint8_t* smB = smem + STAGES * Cfg::A_BYTES;
-  uint8_t* smC = smem + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* smC = smem + STAGES * Cfg::STAGE_BYTES + Cfg::W_BYTES;
   float* smBias = reinterpret_cast<float*>(smC + Cfg::RING_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smC + Cfg::RING_BYTES + Cfg::BIAS_BYTES);
   uint64_t* full = bars;
@@ -156,7 +167,8 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) igemm_kernel(const __grid_co
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint64_t* rfull = bars + 2 * STAGES + 4;  // [NG groups][NBG]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + NG * (NBG > 0 ? NBG : 1));
+  uint64_t* wfull = bars + 2 * STAGES + 4 + NG * (NBG > 0 ? NBG : 1);  // weight-stationary: the resident B tile has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -174,6 +186,7 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) igemm_kernel(const __grid_co
     mbar_init(&tempty[0], 4 * NG * CG);  // CG == 2: the leader's collects the epilogue warps of both CTAs
     mbar_init(&tempty[1], 4 * NG * CG);
     for (int i = 0; i < NG * (NBG > 0 ? NBG : 1); ++i) mbar_init(&rfull[i], 1);
+    mbar_init(wfull, 1);
     fence_barrier_init();
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.b);
@@ -202,6 +215,16 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) igemm_kernel(const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if constexpr (WS) {
+        // the launcher makes the number of units a multiple of n_tiles, so unit + k * nunits keeps ONE N-tile: its weights
+        // (this CTA's half, every k-chunk) are fetched once
+        if (unit < num_tiles) {
+          const int ntile = unit % p.n_tiles;
+          if (cta_rank == 0) mbar_arrive_expect_tx(wfull, 2 * p.k_iters * Cfg::B_BYTES);
+          for (int kit = 0; kit < p.k_iters; ++kit)
+            tma_load_2d_pair(smB + kit * Cfg::B_BYTES, &maps.b, wfull, kit * IG_BK, ntile * BN + cta_rank * (BN / 2));
+        }
+      }
       for (int tile = unit; tile < num_tiles; tile += nunits) {
         const int mt = (tile / p.n_tiles) * CG + cta_rank, ntile = tile % p.n_tiles;
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
@@ -212,7 +235,11 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) igemm_kernel(const __grid_co
           const CUtensorMap* am = &maps.a[sg.src];
           for (int c = 0; c < sg.nchunks; ++c, ++kit) {
             mbar_wait(&empty[stage], phase ^ 1);
-            if constexpr (CG == 2) {
+            if constexpr (WS) {
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::A_BYTES);
+              tma_load_4d_pair(smA + stage * Cfg::A_BYTES, am, &full[stage], sg.chan0 + c * IG_BK, x0 + sg.dx,
+                               y0 + sg.dy, n0 + sg.dn);
+            } else if constexpr (CG == 2) {
               // the leader arms its barrier for the bytes of BOTH CTAs; each CTA loads its A rows and its B half
               if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
               tma_load_4d_pair(smA + stage * Cfg::A_BYTES, am, &full[stage], sg.chan0 + c * IG_BK, x0 + sg.dx,
@@ -240,6 +267,9 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) igemm_kernel(const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       int lt = 0;
+      if constexpr (WS) {
+        if (unit < num_tiles) mbar_wait(wfull, 0);
+      }
       for (int tile = unit; tile < num_tiles; tile += nunits, ++lt) {
         const int acc = lt & 1;
         const uint32_t acc_phase = (lt >> 1) & 1;
@@ -250,7 +280,7 @@ __global__ void __launch_bounds__(64 + 128 * NG, 1) igemm_kernel(const __grid_co
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint64_t ad = umma_desc_kmajor_sw128(smem_u32(smA + stage * Cfg::A_BYTES));
-          const uint64_t bd = umma_desc_kmajor_sw128(smem_u32(smB + stage * Cfg::B_BYTES));
+          const uint64_t bd = umma_desc_kmajor_sw128(smem_u32(smB + (WS ? kit : stage) * Cfg::B_BYTES));
 #pragma unroll
           for (int k = 0; k < IG_BK / 16; ++k) {
             // advance 16 fp16 = 32 B along K inside the 128-B swizzle row: +2 in (addr>>4) units

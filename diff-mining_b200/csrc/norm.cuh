@@ -367,7 +367,7 @@ struct GnStatSrc {
   const float* rec;  // per image [E][C][2] partial (S, Q), then [C] shifts
   int C;
 };
-constexpr int GN_FOLD_MAXC = 2048;
+constexpr int GN_FOLD_MAXC = 2560;
 template <int THREADS, int MINB, int UNR>
 __global__ void __launch_bounds__(THREADS, MINB) gn_fold_apply_kernel(GnStatSrc s0, GnStatSrc s1, int HW, int cpg, int px_per,
                                                                        int VT, int R, int E, const float* __restrict__ gamma,
@@ -476,6 +476,8 @@ __global__ void __launch_bounds__(THREADS, MINB) gn_fold_apply_kernel(GnStatSrc 
     }
     *reinterpret_cast<uint4*>(obase + static_cast<long long>(pxl) * C) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   };
+  // (register double buffering of the batches was measured: fewer resident CTAs cost more than the overlap gains --
+  // 2.96-3.84 ms against 2.81 for the 44 layers of a micro-batch, profiles/r02_experiments/norm_sweep4_prefetch.txt)
   if (first_full) {
 #pragma unroll
     for (int k = 0; k < UNR; ++k) apply(u[k], px + k * R);

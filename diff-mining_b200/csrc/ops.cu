@@ -77,7 +77,8 @@ static int g_xattn = -1, g_prefix = -1, g_ng4 = -1, g_attn3 = -1;
 static int variant_attn3() { return g_attn3 >= 0 ? g_attn3 : env_or("DM_ATTN3", 1); }
 static int variant_igemm_ng4() { return g_ng4 >= 0 ? g_ng4 : env_or("DM_IGEMM_NG4", 1); }
 int variant_prefix_share() { return g_prefix >= 0 ? g_prefix : env_or("DM_PREFIX_SHARE", 1); }
-static int g_gn_epi = -1;
+static int g_gn_epi = -1, g_igemm_ws = -1;
+static int variant_igemm_ws() { return g_igemm_ws >= 0 ? g_igemm_ws : env_or("DM_IGEMM_WS", 0); }
 int gn_epilogue_mode() { return g_gn_epi >= 0 ? g_gn_epi : env_or("DM_GN_EPILOGUE", 3); }
 static int variant_xattn() { return g_xattn >= 0 ? g_xattn : env_or("DM_XATTN", 1); }
 void set_variant(const std::string& name, int value) {
@@ -88,6 +89,7 @@ void set_variant(const std::string& name, int value) {
   else if (name == "igemm_ng4") g_ng4 = value;
   else if (name == "attn3") g_attn3 = value;
   else if (name == "gn_epilogue") g_gn_epi = value;
+  else if (name == "igemm_ws") g_igemm_ws = value;
   else DM_CHECK(false, "unknown kernel variant '" + name + "'");
 }
 
@@ -206,6 +208,16 @@ IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms) {
             (d.cg == 0 && p.m_tiles >= 2 && kit >= 16 &&  // short-K layers are epilogue-bound: pairs only couple them
              static_cast<long long>((p.m_tiles + 1) / 2) * p.n_tiles >= num_sms / 2)))
               ? 2 : 1;
+  // weight-stationary CTA pairs for the short-K (K <= 320) Linears with many M-tiles: the B tile of ONE N-tile stays in shared
+  // memory while the pair walks down M (igemm.cuh: IgCfg).  ws_mode 2 = wherever the shape allows (unit tests).
+  {
+    const int ws_mode = variant_igemm_ws();
+    const int m_units = (p.m_tiles + 1) / 2;
+    const int per_n = p.n_tiles > 0 ? (num_sms / 2) / p.n_tiles : 0;  // pairs per N-tile
+    op.ws = (ws_mode && !op.direct && !d.k_ragged && kit <= IG_WS_KCHUNKS && (op.bn == 256 || op.bn == 160) && per_n >= 1 &&
+             p.m_tiles >= 2 && (ws_mode == 2 || m_units >= 8 * per_n)) ? 1 : 0;
+    if (op.ws) op.cg = 2;
+  }
   DM_CHECK(d.loss == nullptr || (op.direct && !d.out_f32 && d.N >= 4), "igemm: the fused loss epilogue needs the direct fp16 epilogue");
   if (d.gn.rec != nullptr) {
     IgGn& g = p.gn;
@@ -259,19 +271,25 @@ IgemmOp igemm_prepare(const IgemmDesc& d, int num_sms) {
            (ng_mode == 2 || (d.geglu && kit <= 5 && static_cast<long long>(p.m_tiles) * p.n_tiles >= 2 * num_sms))) ? 4 : 2;
   const int tiles = ((p.m_tiles + op.cg - 1) / op.cg) * p.n_tiles;
   op.grid = std::min(tiles, num_sms / op.cg) * op.cg;
+  if (op.ws) {
+    // units = a multiple of n_tiles, so that unit + k * units never changes its N-tile
+    const int per_n = std::min((num_sms / 2) / p.n_tiles, (p.m_tiles + 1) / 2);
+    op.grid = 2 * per_n * p.n_tiles;
+    op.ng = (d.geglu && variant_igemm_ng4()) ? 4 : 2;
+  }
   op.flops = 2.0 * d.Nimg * d.H * d.W * static_cast<double>(d.N) * d.K;
   return op;
 }
 
-template <int BN, bool DIRECT, int CG, int NG = 2>
+template <int BN, bool DIRECT, int CG, int NG = 2, bool WS = false>
 static void igemm_launch_bn(const IgemmOp& op, cudaStream_t s) {
   static bool configured[64] = {};
-  using Cfg = IgCfg<BN, DIRECT, CG, NG>;
+  using Cfg = IgCfg<BN, DIRECT, CG, NG, WS>;
   if (first_use_on_this_device(configured)) {
-    DM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, DIRECT, CG, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    DM_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, DIRECT, CG, NG, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   }
   if (CG == 1) {
-    igemm_kernel<BN, DIRECT, CG, NG><<<op.grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
+    igemm_kernel<BN, DIRECT, CG, NG, WS><<<op.grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
     DM_CUDA(cudaGetLastError());
   } else {
     cudaLaunchConfig_t cfg{};
@@ -286,7 +304,7 @@ static void igemm_launch_bn(const IgemmOp& op, cudaStream_t s) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DM_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<BN, DIRECT, CG, NG>, op.maps, op.p));
+    DM_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<BN, DIRECT, CG, NG, WS>, op.maps, op.p));
   }
 }
 
@@ -300,6 +318,21 @@ void igemm_launch(const IgemmOp& op, cudaStream_t s) {
       case 32: igemm_launch_bn<32, true, 1>(op, s); break;
       case 16: igemm_launch_bn<16, true, 1>(op, s); break;
       default: DM_CHECK(false, "igemm: unsupported BN " + std::to_string(op.bn) + " for the direct epilogue");
+    }
+    return;
+  }
+  if (op.ws) {
+    if (op.ng == 4) {
+      switch (op.bn) {
+        case 256: igemm_launch_bn<256, false, 2, 4, true>(op, s); break;
+        default: DM_CHECK(false, "igemm: unsupported BN " + std::to_string(op.bn) + " for weight-stationary pairs with four groups");
+      }
+      return;
+    }
+    switch (op.bn) {
+      case 256: igemm_launch_bn<256, false, 2, 2, true>(op, s); break;
+      case 160: igemm_launch_bn<160, false, 2, 2, true>(op, s); break;
+      default: DM_CHECK(false, "igemm: unsupported BN " + std::to_string(op.bn) + " for weight-stationary pairs");
     }
     return;
   }
@@ -547,7 +580,7 @@ void gn_launch(const GnDesc& d, cudaStream_t s) {
 
 bool gn_fold_apply_supported(int HW, int C0, int C1) {
   const int C = C0 + C1;
-  return HW % 128 == 0 && C % 32 == 0 && C0 % 8 == 0 && C1 % 8 == 0 && C <= GN_FOLD_MAXC && C / 8 <= 256;
+  return HW % 128 == 0 && C % 32 == 0 && C0 % 8 == 0 && C1 % 8 == 0 && C <= GN_FOLD_MAXC && C / 8 <= 384;
 }
 
 void gn_fold_apply_launch(const GnDesc& d, const float* rec0, const float* rec1, cudaStream_t s) {
@@ -585,6 +618,10 @@ void gn_fold_apply_launch(const GnDesc& d, const float* rec0, const float* rec1,
     DM_CUDA(cudaLaunchKernelEx(&cfg, kernel, s0, s1, d.HW, C / 32, (d.HW + CL - 1) / CL, VT, R, E, d.gamma, d.beta, d.eps, d.silu,
                                d.out));
   };
+  if (VT > 256) {  // 2560 channels (up_blocks.1 at 16x16): one thread per channel vector needs the 384-thread build
+    go(gn_fold_apply_kernel<384, 2, 8>, 384);
+    return;
+  }
   switch (var) {
     case 1: go(gn_fold_apply_kernel<256, 3, 8>, 256); break;
     case 4: go(gn_fold_apply_kernel<256, 5, 4>, 256); break;

@@ -72,6 +72,7 @@ struct IgemmOp {
   int direct = 0;  // 1 = plain global-store epilogue (fp32 output or N-tile < 32 columns)
   int cg = 1;      // CTAs per tile (2 = CTA pair)
   int ng = 2;      // epilogue warpgroups (4 for short-K, epilogue-bound layers)
+  int ws = 0;      // 1 = weight-stationary CTA pairs (short-K Linears with many M-tiles)
   double flops = 0;
 };
 
@@ -130,7 +131,7 @@ int gn_launch_count(int HW, int C);  // kernels gn_launch() issues for this shap
 void gn_launch(const GnDesc& d, cudaStream_t s);
 // GroupNorm over one or two dense sources whose statistics records the producing convs' epilogues left in rec0 / rec1
 // (igemm.cuh: IgGn): fold + apply in one cluster kernel.  d.src0/C0 [, d.src1/C1], d.Nimg, d.HW, gamma / beta / eps / silu /
-// out are read.  Requires HW % 128 == 0, C0 + C1 <= 2048, C0 and C1 multiples of 8, (C0 + C1) % 32 == 0.
+// out are read.  Requires HW % 128 == 0, C0 + C1 <= 2560, C0 and C1 multiples of 8, (C0 + C1) % 32 == 0.
 bool gn_fold_apply_supported(int HW, int C0, int C1);
 void gn_fold_apply_launch(const GnDesc& d, const float* rec0, const float* rec1, cudaStream_t s);
 void layernorm_launch(const __half* x, long long ld_x, const float* gamma, const float* beta, float eps, long long rows,

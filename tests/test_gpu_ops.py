@@ -128,6 +128,45 @@ def test_conv_igemm_four_epilogue_groups(lib, case):
         check(lib, lib.dm_op_set_variant(b"igemm_pair", -1))
 
 
+WS_CASES = [
+    # N, H, W, C0, C1, Cout, ks, stride, vae_pad, rowbias, residual, geglu, silu, f32, bn
+    (3, 64, 64, 320, 0, 320, 1, 1, 0, 0, 1, 0, 0, 0, 0),     # attn.to_out / proj_out: two N-tiles of 160, residual
+    (2, 64, 64, 320, 0, 2560, 1, 1, 0, 0, 0, 1, 0, 0, 0),    # GEGLU: ten N-tiles of 256 (four epilogue groups)
+    (3, 64, 64, 320, 0, 960, 1, 1, 0, 0, 0, 0, 0, 0, 0),     # qkv: six N-tiles, no bias epilogue options
+    (1, 37, 41, 320, 0, 320, 1, 1, 0, 0, 1, 0, 0, 0, 0),     # ragged M, odd number of M-tiles (dummy second tile of the last pair)
+    (1, 16, 16, 64, 0, 640, 1, 1, 0, 0, 0, 0, 1, 0, 0),      # one k-chunk, fewer M-units than CTA pairs, SiLU
+    (2, 16, 16, 256, 0, 256, 1, 1, 0, 1, 1, 0, 0, 0, 0),     # one N-tile of 256, rowbias + residual
+    (5, 32, 32, 320, 0, 320, 3, 1, 0, 1, 0, 0, 0, 0, 0),     # 3x3 (K = 2880): must fall back to the streaming-B kernel
+]
+
+
+@pytest.mark.parametrize("case", WS_CASES, ids=lambda c: "-".join(map(str, c)))
+def test_conv_igemm_weight_stationary(lib, case):
+    """short-K Linears on weight-stationary CTA pairs (igemm.cuh: WS -- the B tile of one N-tile stays in shared memory
+    while the pair walks down M), forced for every eligible shape; bit-identical to the streaming-B kernel"""
+    N, H, W, C0, C1, Cout, ks, stride, vae_pad, rowbias, residual, geglu, silu, f32, bn = case
+    check(lib, lib.dm_op_set_variant(b"igemm_ws", 2))
+    try:
+        test_conv_igemm(lib, case)
+    finally:
+        check(lib, lib.dm_op_set_variant(b"igemm_ws", -1))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(N, H, W, C0, device="cuda", generator=g).half()
+    w = (torch.randn(Cout, C0, ks, ks, device="cuda", generator=g) / math.sqrt(C0 * ks * ks)).half()
+    b = torch.randn(Cout, device="cuda", generator=g)
+    rs = torch.randn(N * H * W, Cout, device="cuda", generator=g).half() if residual else None
+    outs = []
+    for mode in (2, 0):
+        check(lib, lib.dm_op_set_variant(b"igemm_ws", mode))
+        out = torch.full((N * H * W, Cout // 2 if geglu else Cout), float("nan"), device="cuda", dtype=torch.float16)
+        check(lib, lib.dm_op_conv(ptr(x), None, N, H, W, C0, 0, ptr(pack_w(w)), Cout, ks, 1, 0, ptr(b), None, ptr(rs), ptr(out), 0,
+                                  geglu, silu, 0, stream()))
+        torch.cuda.synchronize()
+        outs.append(out)
+    check(lib, lib.dm_op_set_variant(b"igemm_ws", -1))
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_groupnorm_two_kernel_path_matches_fused(lib):
     """the cluster-fused GroupNorm and the stats + apply path agree (both deterministic)"""
     g = torch.Generator(device="cuda").manual_seed(7)
@@ -157,6 +196,7 @@ CONV_GN_CASES = [
     (3, 16, 32, 320, 640, 3, 1, 0, 1, 0.0, 2, -1),      # CTA pairs
     (2, 32, 32, 320, 320, 3, 0, 1, 1, 0.0, 0, 2),       # four epilogue warpgroups
     (2, 32, 32, 320, 320, 1, 0, 1, 0, 0.0, -1, -1),     # 1x1
+    (3, 64, 64, 320, 320, 1, 0, 1, 1, 0.0, -1, -1),     # 1x1 with enough M-tiles for the weight-stationary pair kernel
 ]
 
 

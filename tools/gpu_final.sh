@@ -16,5 +16,5 @@ for t in typ dift typ5 vae; do
   DM_GRAPH=0 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/r02_${t}_launches.csv python tools/profile_target.py $t > gpurun_out/r02_ncu_$t.log 2>&1
 done
 DM_BF=8 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:attention3 -c 1 -o gpurun_out/r02_attn3_d40 -f python tools/profile_target.py attn > gpurun_out/r02_ncu_attn3.log 2>&1
-timeout 900 ncu --set full --clock-control none --profile-from-start off -k regex:"igemm_kernel|attention|gn_fused|layernorm" -o gpurun_out/r02_ops_full -f python tools/profile_target.py ops > gpurun_out/r02_ncu_ops.log 2>&1
+timeout 900 ncu --set full --clock-control none --profile-from-start off -k regex:"igemm_kernel|attention|gn_fused|gn_fold_apply|layernorm" -o gpurun_out/r02_ops_full -f python tools/profile_target.py ops > gpurun_out/r02_ncu_ops.log 2>&1
 ls -la gpurun_out/*.ncu-rep

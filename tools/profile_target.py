@@ -75,6 +75,19 @@ def ops():
         out = torch.empty_like(x)
         return lambda: o.check(lib.dm_op_groupnorm(ptr(x), None, N, HW, C, 0, ptr(g), ptr(b), 1e-5, 1, ptr(out), stream())), (x, g, b, out)
 
+    def conv_gn(N, H, C, silu):
+        """3x3 conv with GroupNorm statistics in its epilogue + the fold/apply GroupNorm kernel (two launches)"""
+        import ctypes
+        P, I = ctypes.c_void_p, ctypes.c_int
+        lib.dm_op_conv_gn.argtypes = [P, I, I, I, I, P, I, I, P, P, P, P, P, ctypes.c_float, I, P, P, P]
+        x = torch.randn(N, H, H, C, device="cuda").half()
+        w = (torch.randn(C, 9 * C, device="cuda") / (9 * C) ** 0.5).half()
+        b, g, bt = torch.randn(C, device="cuda"), torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+        out = torch.empty(N * H * H, C, device="cuda", dtype=torch.float16)
+        gno = torch.empty_like(out)
+        return lambda: o.check(lib.dm_op_conv_gn(ptr(x), N, H, H, C, ptr(w), C, 3, ptr(b), None, None, ptr(g), ptr(bt), 1e-5, silu,
+                                                 ptr(out), ptr(gno), stream())), (x, w, b, g, bt, out, gno)
+
     def ln(rows, C):
         x = torch.randn(rows, C, device="cuda").half()
         g = torch.randn(C, device="cuda")
@@ -84,7 +97,7 @@ def ops():
 
     targets = [conv(32, 64, 64, 320, 320, 3), conv(32, 64, 64, 320, 2560, 1, geglu=1), conv(32, 64, 64, 320, 320, 1, res=True),
                conv(32, 16, 16, 1280, 1280, 3), conv(32, 32, 32, 1280, 1280, 3), attn(32, 4096, 40), attn(32, 1024, 80),
-               xattn(32, 4096, 40), gn(32, 4096, 320), ln(32 * 4096, 320)]
+               xattn(32, 4096, 40), gn(32, 4096, 320), ln(32 * 4096, 320), conv_gn(32, 64, 320, 1)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for f, _ in targets:
         for _ in range(2):

@@ -13,10 +13,11 @@ WANT = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum",
         "dram__bytes_write.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "launch__registers_per_thread", "launch__cluster_size", "smsp__inst_executed.sum", "launch__grid_size", "launch__block_size"]
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__cluster_size", "smsp__inst_executed.sum", "launch__grid_size", "launch__block_size"]
 TARGETS = ["conv3x3 320->320 @64x64 x32", "GEGLU 320->2560 @64x64 x32", "1x1 320->320 +res @64x64 x32", "conv3x3 1280->1280 @16x16 x32",
            "conv3x3 1280->1280 @32x32 x32 (CTA pairs)", "self-attn d=40 T=4096 x32", "self-attn d=80 T=1024 x32",
-           "cross-attn d=40 T=4096 x 77 keys x32", "GroupNorm+SiLU 320ch @64x64 x32", "LayerNorm 320 x 131072 rows"]
+           "cross-attn d=40 T=4096 x 77 keys x32", "GroupNorm+SiLU 320ch @64x64 x32 (stand-alone)", "LayerNorm 320 x 131072 rows",
+           "conv3x3 320->320 @64x64 x32 + GroupNorm statistics in the epilogue", "GroupNorm+SiLU 320ch @64x64 x32 (fold + apply)"]
 
 
 def rows_of(rep):
