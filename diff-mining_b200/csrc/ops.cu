@@ -80,7 +80,7 @@ int variant_prefix_share() { return g_prefix >= 0 ? g_prefix : env_or("DM_PREFIX
 static int g_gn_epi = -1, g_igemm_ws = -1;
 static int variant_igemm_ws() { return g_igemm_ws >= 0 ? g_igemm_ws : env_or("DM_IGEMM_WS", 0); }
 int gn_epilogue_mode() { return g_gn_epi >= 0 ? g_gn_epi : env_or("DM_GN_EPILOGUE", 3); }
-static int variant_xattn() { return g_xattn >= 0 ? g_xattn : env_or("DM_XATTN", 1); }
+static int variant_xattn() { return g_xattn >= 0 ? g_xattn : env_or("DM_XATTN", 2); }
 void set_variant(const std::string& name, int value) {
   if (name == "igemm_pair") g_igemm_pair = value;
   else if (name == "gn_fused") g_gn_fused = value;
@@ -450,6 +450,24 @@ static void xattn_launch_d(const AttnOp& op, cudaStream_t s) {
   xattention_kernel<D><<<op.grid, 128, Cfg::SMEM_BYTES, s>>>(op.maps, op.p);
   DM_CUDA(cudaGetLastError());
 }
+template <int D>
+static void xattn2_launch_d(const AttnOp& op, cudaStream_t s) {
+  static bool configured[64] = {};
+  using Cfg = XAttn2Cfg<D>;
+  if (first_use_on_this_device(configured)) {
+    DM_CUDA(cudaFuncSetAttribute(xattention2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  }
+  int dev = 0, sms = 0;
+  DM_CUDA(cudaGetDevice(&dev));
+  DM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int nq = (op.p.Tq + 127) / 128;
+  const long long total_q = static_cast<long long>(nq) * op.p.B;  // (batch, query block) pairs; every CTA serves one head
+  DM_CHECK(total_q < (1ll << 31), "cross-attention: too many query blocks");
+  const long long ranges = std::max<long long>(1, std::min<long long>(total_q, static_cast<long long>(sms) * Cfg::CTAS_PER_SM / op.p.heads));
+  const unsigned grid = static_cast<unsigned>(ranges * op.p.heads);
+  xattention2_kernel<D><<<grid, 128, Cfg::SMEM_BYTES, s>>>(op.maps, op.p, nq, static_cast<int>(total_q));
+  DM_CUDA(cudaGetLastError());
+}
 static void vattn_launch(const AttnOp& op, cudaStream_t s) {
   static bool configured[64] = {};
   if (first_use_on_this_device(configured)) {
@@ -464,9 +482,13 @@ void attn_launch(const AttnOp& op, cudaStream_t s) {
     return;
   }
   if (op.xattn) {
+    // xattn = 2 (default): persistent kernel at head_dim 40 (0.150 vs 0.185 ms per 64x64 layer at Bf 54); at head_dim 80 it
+    // holds two CTAs per SM and measured 10 % slower than one CTA per query block, so it is only used there with xattn = 3
+    // (tests).  xattn = 1: one CTA per query block everywhere.
+    const int xv = variant_xattn();
     switch (op.D) {
-      case 40: xattn_launch_d<40>(op, s); break;
-      case 80: xattn_launch_d<80>(op, s); break;
+      case 40: xv >= 2 ? xattn2_launch_d<40>(op, s) : xattn_launch_d<40>(op, s); break;
+      case 80: xv >= 3 ? xattn2_launch_d<80>(op, s) : xattn_launch_d<80>(op, s); break;
       case 160: xattn_launch_d<160>(op, s); break;
       default: DM_CHECK(false, "attention: unsupported head_dim");
     }

@@ -155,7 +155,10 @@ int dm_op_layernorm(const void* x, int64_t rows, int C, const float* gamma, cons
  *               2 = wherever the tile shape allows (N-tile >= 128, fp16 output)
  *   igemm_ng4   1 = four epilogue warpgroups for short-K (epilogue-bound) layers, 0 = always two, 2 = wherever possible
  *   gn_fused    1 = cluster-fused single-pass GroupNorm for images that fit in L2, 0 = two-kernel path
- *   xattn       1 = short-key-set cross-attention kernel (P in tensor memory), 0 = generic flash kernel
+ *   xattn       2 = persistent short-key-set cross-attention kernel at head_dim 40 (default), 3 = also at head_dim 80,
+ *               1 = the same arithmetic with one CTA per query block (bit-identical), 0 = generic flash kernel
+ *   igemm_ws    1 = weight-stationary CTA pairs for K <= 320 Linears with many M-tiles (measured slower: default 0),
+ *               2 = wherever the shape allows (tests)
  *   attn3       persistent self-attention kernel (attention3.cuh): 1 = two softmax threads per query row, 2 = one thread per
  *               row; 0 = one CTA per 256-query block (attention2.cuh)
  *   gn_epilogue bit mask: 1 = 3x3 convs, 2 = 1x1 convs / Linears form the GroupNorm statistics of their output in the

@@ -300,6 +300,44 @@ def test_flash_attention_variants(lib, case):
             check(lib, lib.dm_op_set_variant(b"attn3", -1))
 
 
+XATTN_CASES = [
+    # B, Tq, Tk, D: several items per persistent CTA, context-slot changes inside a CTA's range, ragged query blocks
+    (54, 4096, 77, 40), (54, 1024, 77, 80), (7, 1000, 77, 40), (9, 300, 77, 80), (3, 128, 77, 40), (1, 77, 60, 80), (160, 256, 77, 40),
+]
+
+
+@pytest.mark.parametrize("case", XATTN_CASES, ids=lambda c: "-".join(map(str, c)))
+def test_cross_attention_persistent_matches_one_shot(lib, case):
+    """text cross-attention: the persistent kernel (one head and a contiguous range of (batch, query block) pairs per CTA, K / V kept while the
+    context slot does not change, next Q prefetched) against SDPA and bit-identical to the one-CTA-per-block
+    kernel (xattn = 1)"""
+    B, T, Tk, D = case
+    heads, nslots = 8, 5
+    C = heads * D
+    g = torch.Generator(device="cuda").manual_seed(7 + B + T + D)
+    q = torch.randn(B, T, C, device="cuda", generator=g).half()
+    kv = torch.randn(nslots, Tk, 2 * C, device="cuda", generator=g).half()
+    kvi = torch.randint(0, nslots, (B,), device="cuda", generator=g, dtype=torch.int32)
+    outs = []
+    for mode in (3, 1):  # 3 = persistent kernel at head_dim 40 and 80 (the default, 2, uses it at head_dim 40 only)
+        check(lib, lib.dm_op_set_variant(b"xattn", mode))
+        out = torch.full((B, T, C), float("nan"), device="cuda", dtype=torch.float16)
+        check(lib, lib.dm_op_attention(ptr(q), ptr(kv[..., :C]), ptr(kv[..., C:]), C, 2 * C, 2 * C, T * C, Tk * 2 * C, Tk * 2 * C, B,
+                                       heads, D, T, Tk, nslots, ptr(kvi), ptr(out), C, stream()))
+        torch.cuda.synchronize()
+        outs.append(out)
+    check(lib, lib.dm_op_set_variant(b"xattn", -1))
+    nb = min(B, 6)
+    kk, vv = kv[kvi[:nb].long(), :, :C], kv[kvi[:nb].long(), :, C:]
+    qh = q[:nb].float().reshape(nb, T, heads, D).transpose(1, 2)
+    kh = kk.float().reshape(nb, Tk, heads, D).transpose(1, 2)
+    vh = vv.float().reshape(nb, Tk, heads, D).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(nb, T, C)
+    assert torch.isfinite(outs[0]).all()
+    assert max_rel(outs[0][:nb], ref) < 2e-3
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("B,T", [(2, 1024), (1, 45), (3, 425), (1, 4096)])
 def test_vae_single_head_attention(lib, B, T):
     """one 512-wide head (VAE mid block) on the flash kernel: two CTAs per query tile, any token count"""

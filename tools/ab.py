@@ -1,6 +1,7 @@
 """A/B timing + correctness of kernel variants through the op-level C ABI (development aid, run under gpurun).
    python tools/ab.py attn      self-attention shapes of the U-Net, every value of the `attn3` switch
    python tools/ab.py gn        GroupNorm shapes, fused vs two-kernel
+   python tools/ab.py xattn     text cross-attention: one CTA per query block vs the persistent kernel
    python tools/ab.py norm      the streaming normalisation kernels at the U-Net's big shapes (LayerNorm, conv + epilogue
                                 statistics + fold/apply GroupNorm, stand-alone GroupNorm): event times, or the target of an
                                 ncu capture (variants are per-process: DM_LN_VAR, DM_GNFA_VAR, DM_GNFA_CL)
@@ -117,6 +118,22 @@ def stress():
         o.check(lib.dm_op_set_variant(b"attn3", -1))
 
 
+def xattn():
+    """text cross-attention at the U-Net's shapes: one-CTA-per-block kernel (xattn = 1) vs persistent kernel (xattn = 2)"""
+    for (B, T, D) in [(54, 4096, 40), (54, 1024, 80), (54, 256, 160), (15, 16384, 40)]:
+        C = 8 * D
+        q = torch.randn(B, T, C, device="cuda").half()
+        kv = torch.randn(2, 77, 2 * C, device="cuda").half()
+        idx = (torch.arange(B, device="cuda", dtype=torch.int32) % 2).contiguous()
+        out = torch.empty(B, T, C, device="cuda", dtype=torch.float16)
+        args = (ptr(q), ptr(kv[..., :C]), ptr(kv[..., C:]), C, 2 * C, 2 * C, T * C, 77 * 2 * C, 77 * 2 * C, B, 8, D, T, 77, 2, ptr(idx), ptr(out), C, stream())
+        for v_ in (1, 3):
+            o.check(lib.dm_op_set_variant(b"xattn", v_))
+            med, mn = timeit(lambda: o.check(lib.dm_op_attention(*args)))
+            print(f"XATTN B={B} T={T} D={D} xattn={v_}: {med:8.4f} ms (min {mn:.4f})  {2.0 * q.numel() * 2 / med / 1e6:7.1f} GB/s algorithmic (Q in + O out)", flush=True)
+        o.check(lib.dm_op_set_variant(b"xattn", -1))
+
+
 def norm():
     lib.dm_op_conv_gn.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + \
         [ctypes.c_void_p] * 5 + [ctypes.c_float, ctypes.c_int] + [ctypes.c_void_p] * 3
@@ -143,4 +160,4 @@ def norm():
 
 
 if __name__ == "__main__":
-    {"attn": attn, "gn": gn, "stress": stress, "norm": norm}[sys.argv[1]]()
+    {"attn": attn, "gn": gn, "stress": stress, "norm": norm, "xattn": xattn}[sys.argv[1]]()
