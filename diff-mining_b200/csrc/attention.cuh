@@ -407,45 +407,53 @@ __global__ void __launch_bounds__(128) xattention2_kernel(const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);  // this thread's lane quarter
 
-  auto load_q = [&](int idx, int buf) {  // thread 0
-    const int b = idx / nq, q0 = (idx % nq) * 128;
+  // ---- thread 0: producer + MMA issuer.  issue_s(i) = make item i's K / V and Q resident and issue S = Q K^T for it.  It is
+  // called for item i + 1 right after item i's P V MMA has completed, so the S MMA (and a rare K / V reload) runs while the
+  // 128 threads read item i's O out of tensor memory and store it; the Q tile of item i + 2 is requested at the same point.
+  int cur_b = -1, cur_kvb = -1;  // the image whose slot was looked up last / the context slot sK, sV hold
+  uint32_t kv_phase = 0;
+  auto load_q = [&](int idx, int buf) {
+    const int b = idx / nq, q0 = (idx - b * nq) * 128;
     mbar_arrive_expect_tx(&bar_q[buf], Cfg::Q_BYTES);
     for (int c = 0; c < NCH; ++c) tma_load_4d(sQ + buf * Cfg::Q_BYTES + c * 16384, &maps.q, &bar_q[buf], c * 64, head, q0, b);
   };
-  int cur_kvb = -1;  // thread 0: the context slot sK / sV hold (the head never changes)
-  uint32_t kv_phase = 0;
-  if (tid == 0) load_q(i0, 0);
-
-  for (int i = i0; i < i1; ++i) {
-    const int li = i - i0, qb = li & 1;
-    const int b = i / nq, q0 = (i % nq) * 128;
-    if (tid == 0) {
-      // every MMA of the previous item has completed (this thread waited on bar_s and bar_o), so sK / sV and the other Q
-      // buffer are free
+  auto issue_s = [&](int idx) {
+    // every earlier MMA has completed (the caller waited on bar_o of the previous item): sK / sV may be replaced
+    const int li = idx - i0, qb = li & 1;
+    const int b = idx / nq;
+    if (b != cur_b) {
+      cur_b = b;
       const int kvb = p.kv_index ? p.kv_index[b] : b;
-      const bool new_kv = kvb != cur_kvb;
-      if (new_kv) {
+      if (kvb != cur_kvb) {
+        cur_kvb = kvb;
         mbar_arrive_expect_tx(bar_kv, 2 * Cfg::KV_BYTES);
         for (int c = 0; c < NCH; ++c) tma_load_4d(sK + c * TK * 128, &maps.k, bar_kv, c * 64, head, 0, kvb);
         for (int c = 0; c < NCH; ++c) tma_load_4d(sV + c * TK * 128, &maps.v, bar_kv, c * 64, head, 0, kvb);
-        cur_kvb = kvb;
-      }
-      if (i + 1 < i1) load_q(i + 1, qb ^ 1);
-      constexpr uint32_t idesc_s = umma_idesc_f16(TK, false);
-      mbar_wait(&bar_q[qb], (li >> 1) & 1);
-      if (new_kv) {
         mbar_wait(bar_kv, kv_phase);
         kv_phase ^= 1;
       }
-      tc_fence_after();
-#pragma unroll
-      for (int ks = 0; ks < DK / 16; ++ks) {
-        const uint64_t ad = umma_desc_kmajor_sw128(smem_u32(sQ + qb * Cfg::Q_BYTES + (ks >> 2) * 16384)) + 2 * (ks & 3);
-        const uint64_t bd = umma_desc_kmajor_sw128(smem_u32(sK + (ks >> 2) * TK * 128)) + 2 * (ks & 3);
-        umma_f16(tmem_base, ad, bd, idesc_s, ks != 0 ? 1u : 0u);
-      }
-      umma_commit(bar_s);
     }
+    constexpr uint32_t idesc_s = umma_idesc_f16(TK, false);
+    mbar_wait(&bar_q[qb], (li >> 1) & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int ks = 0; ks < DK / 16; ++ks) {
+      const uint64_t ad = umma_desc_kmajor_sw128(smem_u32(sQ + qb * Cfg::Q_BYTES + (ks >> 2) * 16384)) + 2 * (ks & 3);
+      const uint64_t bd = umma_desc_kmajor_sw128(smem_u32(sK + (ks >> 2) * TK * 128)) + 2 * (ks & 3);
+      umma_f16(tmem_base, ad, bd, idesc_s, ks != 0 ? 1u : 0u);
+    }
+    umma_commit(bar_s);
+  };
+  if (tid == 0) {
+    load_q(i0, 0);
+    if (i0 + 1 < i1) load_q(i0 + 1, 1);
+    issue_s(i0);
+  }
+
+  int b = i0 / nq, qblk = i0 - b * nq;
+  for (int i = i0; i < i1; ++i) {
+    const int li = i - i0;
+    const int q0 = qblk * 128;
     mbar_wait(bar_s, li & 1);
     tc_fence_after();
     // ---- softmax of row `tid` over the Tk valid keys, in registers (same arithmetic as xattention_kernel)
@@ -486,23 +494,32 @@ __global__ void __launch_bounds__(128) xattention2_kernel(const __grid_constant_
     }
     mbar_wait(bar_o, li & 1);
     tc_fence_after();
+    if (tid == 0 && i + 1 < i1) {
+      // S / P columns and this item's Q buffer are free: start the next item's S now, refill the Q buffer with item i + 2
+      issue_s(i + 1);
+      if (i + 2 < i1) load_q(i + 2, li & 1);
+    }
     const int q = q0 + tid;
     const float inv = 1.f / lsum;
     __half* orow = p.out + (static_cast<long long>(b) * p.Tq + q) * p.ld_out + head * D;
+    uint32_t o[Cfg::DK];  // the S MMA of the next item writes columns [0, TK) only: O at [TK, TK + DK) is still this item's
 #pragma unroll
-    for (int c0 = 0; c0 < D; c0 += 8) {
-      uint32_t o[8];
-      tmem_ld_x8(t_row + Cfg::O_COL + c0, o);
-      tmem_wait_ld();
-      if (q < p.Tq) {
+    for (int c0 = 0; c0 < DK; c0 += 8) tmem_ld_x8(t_row + Cfg::O_COL + c0, o + c0);
+    tmem_wait_ld();
+    if (q < p.Tq) {
+#pragma unroll
+      for (int c0 = 0; c0 < D; c0 += 8)
         *reinterpret_cast<uint4*>(orow + c0) =
-            make_uint4(pack_h2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv),
-                       pack_h2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv),
-                       pack_h2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv),
-                       pack_h2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv));
-      }
+            make_uint4(pack_h2(__uint_as_float(o[c0]) * inv, __uint_as_float(o[c0 + 1]) * inv),
+                       pack_h2(__uint_as_float(o[c0 + 2]) * inv, __uint_as_float(o[c0 + 3]) * inv),
+                       pack_h2(__uint_as_float(o[c0 + 4]) * inv, __uint_as_float(o[c0 + 5]) * inv),
+                       pack_h2(__uint_as_float(o[c0 + 6]) * inv, __uint_as_float(o[c0 + 7]) * inv));
     }
-    tc_fence_before();  // orders these tensor-memory reads before the next item's barrier / MMAs
+    tc_fence_before();  // orders these tensor-memory reads before the next item's barrier / P V MMA
+    if (++qblk == nq) {
+      qblk = 0;
+      ++b;
+    }
   }
   __syncthreads();
   if (warp == 0) {
