@@ -361,7 +361,10 @@ __global__ void __launch_bounds__(384, MINB) gn_fused_kernel(NormSrc s0, NormSrc
 //           shared memory of all CTAs of the image (distributed shared memory)
 //   cluster.sync (the only one)
 //   apply   CTA `rank` normalises (+SiLU) pixels [rank*px_per, (rank+1)*px_per): 1 read + 1 write of the activation.
-// Deterministic and batch-invariant: the entry order, slice count (a function of C) and trees are fixed.
+// Large images (128x128 latents: few images per micro-batch) are split over gridDim.z clusters, each folding the (small)
+// records again and applying to its own quarter of the pixels, so the pass still fills the machine.
+// Deterministic and batch-invariant: the entry order, slice count (a function of C), split count (a function of HW) and
+// trees are fixed.
 struct GnStatSrc {
   const __half* x;   // dense [Nimg][HW][C]
   const float* rec;  // per image [E][C][2] partial (S, Q), then [C] shifts
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gn_fold_apply_kernel(GnStatSrc 
   const bool active = tid < VT * R;
   const int r = tid / VT, vt = tid % VT;
   const int c = vt << 3;
-  const int p0 = min(HW, rank * px_per), p1 = min(HW, p0 + px_per);
+  const int p0 = min(HW, (static_cast<int>(blockIdx.z) * CL + rank) * px_per), p1 = min(HW, p0 + px_per);
   const bool in0 = c < s0.C;
   const long long ps = in0 ? s0.C : s1.C;  // pixel stride of this thread's source
   const __half* base = (in0 ? s0.x + c : s1.x + (c - s0.C)) + static_cast<long long>(n) * HW * ps;
@@ -410,10 +413,12 @@ __global__ void __launch_bounds__(THREADS, MINB) gn_fold_apply_kernel(GnStatSrc 
     const float2* pp = reinterpret_cast<const float2*>((f0 ? s0.rec : s1.rec) + static_cast<long long>(n) * (2 * E + 1) * Cs) + lc;
     float s = 0.f, q = 0.f;
     int e = sl;
-    for (; e + 3 * NS < E; e += 4 * NS) {
-      const float2 v0 = __ldcg(pp + static_cast<long long>(e) * Cs), v1 = __ldcg(pp + static_cast<long long>(e + NS) * Cs);
-      const float2 v2 = __ldcg(pp + static_cast<long long>(e + 2 * NS) * Cs), v3 = __ldcg(pp + static_cast<long long>(e + 3 * NS) * Cs);
-      s += v0.x; q += v0.y; s += v1.x; q += v1.y; s += v2.x; q += v2.y; s += v3.x; q += v3.y;
+    for (; e + 7 * NS < E; e += 8 * NS) {  // eight independent loads in flight, added in index order
+      float2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldcg(pp + static_cast<long long>(e + k * NS) * Cs);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s += v[k].x; q += v[k].y; }
     }
     for (; e < E; e += NS) {
       const float2 v = __ldcg(pp + static_cast<long long>(e) * Cs);

@@ -625,7 +625,9 @@ void gn_fold_apply_launch(const GnDesc& d, const float* rec0, const float* rec1,
     static bool configured[64] = {};
     if (first_use_on_this_device(configured)) DM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(CL, d.Nimg, 1);
+    // clusters per image: a function of HW alone (batch invariance); 128x128 latents come few per micro-batch
+    const int splits = d.HW >= 16384 ? 4 : d.HW >= 8192 ? 2 : 1;
+    cfg.gridDim = dim3(CL, d.Nimg, splits);
     cfg.blockDim = dim3(threads, 1, 1);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = s;
@@ -637,8 +639,8 @@ void gn_fold_apply_launch(const GnDesc& d, const float* rec0, const float* rec1,
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const int R = std::max(1, threads / VT);
-    DM_CUDA(cudaLaunchKernelEx(&cfg, kernel, s0, s1, d.HW, C / 32, (d.HW + CL - 1) / CL, VT, R, E, d.gamma, d.beta, d.eps, d.silu,
-                               d.out));
+    const int px_per = (d.HW + CL * splits - 1) / (CL * splits);
+    DM_CUDA(cudaLaunchKernelEx(&cfg, kernel, s0, s1, d.HW, C / 32, px_per, VT, R, E, d.gamma, d.beta, d.eps, d.silu, d.out));
   };
   if (VT > 256) {  // 2560 channels (up_blocks.1 at 16x16): one thread per channel vector needs the 384-thread build
     go(gn_fold_apply_kernel<384, 2, 8>, 384);

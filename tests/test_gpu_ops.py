@@ -197,6 +197,8 @@ CONV_GN_CASES = [
     (2, 32, 32, 320, 320, 3, 0, 1, 1, 0.0, 0, 2),       # four epilogue warpgroups
     (2, 32, 32, 320, 320, 1, 0, 1, 0, 0.0, -1, -1),     # 1x1
     (3, 64, 64, 320, 320, 1, 0, 1, 1, 0.0, -1, -1),     # 1x1 with enough M-tiles for the weight-stationary pair kernel
+    (2, 128, 64, 320, 320, 3, 1, 0, 1, 0.0, -1, -1),    # 8192 pixels: two fold + apply clusters per image
+    (1, 128, 128, 320, 320, 3, 0, 1, 1, 0.0, -1, -1),   # 16384 pixels (config 5): four clusters per image
 ]
 
 
