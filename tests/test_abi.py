@@ -37,6 +37,22 @@ def test_ctypes_table_matches_header():
     assert lib.dm_abi_version() == 1
 
 
+def test_variant_switches_documented_in_the_header_are_accepted():
+    """every kernel-variant name dm_abi.h documents is known to the library (a host-side switch: no GPU needed) and an
+    unknown one is an error with a message, not a silent no-op"""
+    from diff_mining_b200 import _abi
+
+    hdr = open(os.path.join(ROOT, "include", "dm_abi.h")).read()
+    doc = hdr[hdr.index("kernel-variant switches"):hdr.index("int dm_op_set_variant")]
+    names = re.findall(r"^ \*   ([a-z0-9_]+) ", doc, flags=re.M)
+    assert {"igemm_pair", "igemm_ng4", "igemm_ws", "gn_fused", "gn_epilogue", "xattn", "attn3", "prefix_share"} <= set(names)
+    lib = _abi.load()
+    for n in names:
+        assert lib.dm_op_set_variant(n.encode(), -1) == 0, n
+    assert lib.dm_op_set_variant(b"no_such_variant", 1) != 0
+    assert b"no_such_variant" in lib.dm_last_error()
+
+
 def test_no_cpu_fallback():
     import torch
 
