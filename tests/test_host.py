@@ -228,3 +228,40 @@ def test_context_slots_many_categories():
         s = cs.acquire([_ctx(c), uncond])
         assert s[0] != s[1]
     assert len(fe.uploaded) == 366   # the unconditional context stayed resident the whole time (most recently used)
+
+
+def test_groupnorm_shifted_sum_algebra_two_sources():
+    """the algebra the GroupNorm kernels fold with (norm.cuh: S_c = sum(x - k_c), Q_c = sum((x - k_c)^2) per channel with an
+    ARBITRARY per-(image, channel) shift k_c, partials over disjoint pixel sets, groups that straddle two concatenated
+    sources) restated in numpy float64 and checked against torch.group_norm on cat(src0, src1) -- large channel means
+    included, where E[x^2] - E[x]^2 in fp32 would cancel"""
+    g = np.random.default_rng(11)
+    HW, C0, C1, groups = 256, 80, 48, 32      # cpg = 4: group boundaries do not care about the source boundary
+    x0 = g.normal(size=(HW, C0)) + g.normal(size=C0) * 50.0
+    x1 = g.normal(size=(HW, C1)) * 3.0 - 20.0
+    xs, out = (x0, x1), []
+    cpg = (C0 + C1) // groups
+    # per-source records: 8 partial entries (disjoint pixel blocks) of (S, Q) about a shift that is NOT the mean
+    S, Q, K = [], [], []
+    for x in xs:
+        k = x[0] + g.normal(size=x.shape[1])                     # "value at the image's first pixel" + anything
+        parts = np.split(np.arange(HW), 8)
+        s = np.stack([(x[p] - k).sum(0) for p in parts])
+        q = np.stack([((x[p] - k) ** 2).sum(0) for p in parts])
+        S.append(s.astype(np.float32).sum(0, dtype=np.float32))   # fp32 fold in index order, like the kernel
+        Q.append(q.astype(np.float32).sum(0, dtype=np.float32))
+        K.append(k.astype(np.float32))
+    S, Q, K = (np.concatenate(v).astype(np.float64) for v in (S, Q, K))
+    n = float(HW)
+    mean = np.empty(groups)
+    rstd = np.empty(groups)
+    for gi in range(groups):
+        c = slice(gi * cpg, (gi + 1) * cpg)
+        mean[gi] = (S[c] + n * K[c]).sum() / (n * cpg)
+        d = mean[gi] - K[c]
+        m2 = (Q[c] - 2.0 * d * S[c] + n * d * d).sum()
+        rstd[gi] = 1.0 / np.sqrt(max(m2 / (n * cpg), 0.0) + 1e-5)
+    xcat = np.concatenate(xs, axis=1)
+    got = (xcat - np.repeat(mean, cpg)) * np.repeat(rstd, cpg)
+    ref = torch.nn.functional.group_norm(torch.from_numpy(xcat.T[None].copy()), groups, eps=1e-5)[0].T.numpy()
+    assert np.abs(got - ref).max() < 2e-4
